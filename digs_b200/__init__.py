@@ -1,0 +1,13 @@
+"""digs_b200 -- B200-native (sm_100a) hot path for DiGS: fused value/gradient/Laplacian jets of the sine MLP,
+the DiGSLoss reverse pass through them, and the dense-grid SDF query.  Drop-in names mirror the reference:
+
+    from digs_b200 import DiGSNetwork, DiGSLoss, implicit2mesh
+
+All arithmetic runs in libdigs_b200.so (C-ABI in include/digs_b200.h); there is no CPU fallback.
+"""
+from .network import DiGSNetwork, Decoder, FCBlock, Sine
+from .losses import DiGSLoss
+from .grid import implicit2mesh, get_3d_grid, grid_axes, grid_query, slab_range
+
+__all__ = ["DiGSNetwork", "Decoder", "FCBlock", "Sine", "DiGSLoss", "implicit2mesh", "get_3d_grid", "grid_axes",
+           "grid_query", "slab_range"]

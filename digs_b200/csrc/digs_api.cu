@@ -1,0 +1,174 @@
+// C-ABI of libdigs_b200.so (see include/digs_b200.h): argument checking and dispatch on precision mode.
+#include "digs_internal.h"
+#include <cstdarg>
+#include <cstdio>
+
+namespace digs {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int check_net(const DigsNet* net) {
+    if (!net) { set_error("net is NULL"); return DIGS_EINVAL; }
+    if (net->d != 2 && net->d != 3) { set_error("net.d must be 2 or 3 (got %d)", net->d); return DIGS_EINVAL; }
+    if (net->H < 64 || net->H > 1024 || (net->H % 64)) {
+        set_error("net.H must be a multiple of 64 in [64,1024] (got %d)", net->H);
+        return DIGS_EINVAL;
+    }
+    if (net->Lh < 1 || net->Lh + 2 > DIGS_MAX_LAYERS) {
+        set_error("net.Lh must be in [1,%d] (got %d)", DIGS_MAX_LAYERS - 2, net->Lh);
+        return DIGS_EINVAL;
+    }
+    if (net->head != DIGS_HEAD_IDENTITY && net->head != DIGS_HEAD_SQRT) { set_error("bad head"); return DIGS_EINVAL; }
+    if (net->w0_stride < net->d) { set_error("w0_stride < d"); return DIGS_EINVAL; }
+    for (int l = 0; l <= net->Lh + 1; ++l)
+        if (!net->W[l] || !net->b[l]) { set_error("net.W[%d]/b[%d] is NULL", l, l); return DIGS_EINVAL; }
+    return DIGS_OK;
+}
+static int check_mode(int mode) {
+    if (mode == DIGS_MODE_FP32) return DIGS_OK;
+    if (mode == DIGS_MODE_BF16X2 || mode == DIGS_MODE_BF16) {
+        set_error("precision mode %d (tcgen05) is not built into this library yet", mode);
+        return DIGS_ENOTIMPL;
+    }
+    set_error("unknown precision mode %d", mode);
+    return DIGS_EINVAL;
+}
+}  // namespace digs
+
+using namespace digs;
+
+extern "C" {
+
+int digs_abi_version(void) { return DIGS_ABI_VERSION; }
+const char* digs_last_error(void) { return g_err; }
+
+size_t digs_saved_bytes(const DigsNet* net, int64_t n, int want_lap, int mode) {
+    if (check_net(net) || check_mode(mode) || n < 0) return 0;
+    return simt::saved_bytes(net, n, want_lap);
+}
+size_t digs_forward_workspace_bytes(const DigsNet* net, int64_t n, int want_lap, int mode) {
+    if (check_net(net) || check_mode(mode) || n < 0) return 0;
+    return simt::fwd_ws_bytes(net, n, want_lap);
+}
+size_t digs_backward_workspace_bytes(const DigsNet* net, int64_t n, int want_lap, int mode) {
+    if (check_net(net) || check_mode(mode) || n < 0) return 0;
+    return simt::bwd_ws_bytes(net, n, want_lap);
+}
+size_t digs_value_workspace_bytes(const DigsNet* net, int64_t n, int mode) {
+    if (check_net(net) || check_mode(mode) || n < 0) return 0;
+    return simt::value_ws_bytes(net, n);
+}
+size_t digs_grid_workspace_bytes(const DigsNet* net, int mode) {
+    if (check_net(net) || check_mode(mode)) return 0;
+    return simt::grid_ws_bytes(net);
+}
+
+int digs_jet_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_stride, const float* shape_bias,
+                     int64_t pts_per_shape, int want_lap, float* f, float* grad, float* lap, void* saved,
+                     size_t saved_bytes, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+    int rc;
+    if ((rc = check_net(net)) || (rc = check_mode(mode))) return rc;
+    if (n < 0 || xyz_stride < net->d) { set_error("jet_forward: bad n/xyz_stride"); return DIGS_EINVAL; }
+    if (n == 0) return DIGS_OK;
+    if (!xyz || !f || !grad || (want_lap && !lap)) { set_error("jet_forward: NULL buffer"); return DIGS_EINVAL; }
+    if (shape_bias && pts_per_shape <= 0) { set_error("jet_forward: pts_per_shape <= 0"); return DIGS_EINVAL; }
+    if (saved && saved_bytes < simt::saved_bytes(net, n, want_lap)) {
+        set_error("jet_forward: saved buffer too small (%zu < %zu)", saved_bytes, simt::saved_bytes(net, n, want_lap));
+        return DIGS_ENOSPACE;
+    }
+    size_t need = simt::fwd_ws_bytes(net, n, want_lap);
+    if (!workspace || workspace_bytes < need) {
+        set_error("jet_forward: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return DIGS_ENOSPACE;
+    }
+    return simt::jet_forward(net, xyz, n, xyz_stride, shape_bias, pts_per_shape, want_lap, f, grad, lap, saved,
+                             workspace, (cudaStream_t)stream);
+}
+
+int digs_jet_backward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_stride, const float* shape_bias,
+                      int64_t pts_per_shape, int want_lap, const float* f_bar, const float* grad_bar,
+                      const float* lap_bar, const void* saved, size_t saved_bytes, void* workspace,
+                      size_t workspace_bytes, const DigsGrads* grads, float* shape_bias_grad, int mode,
+                      void* stream) {
+    int rc;
+    if ((rc = check_net(net)) || (rc = check_mode(mode))) return rc;
+    if (n < 0 || xyz_stride < net->d) { set_error("jet_backward: bad n/xyz_stride"); return DIGS_EINVAL; }
+    if (n == 0) return DIGS_OK;
+    if (!xyz || !saved || !grads) { set_error("jet_backward: NULL buffer"); return DIGS_EINVAL; }
+    for (int l = 0; l <= net->Lh + 1; ++l)
+        if (!grads->dW[l] || !grads->db[l]) { set_error("jet_backward: grads.dW[%d]/db[%d] NULL", l, l); return DIGS_EINVAL; }
+    if (shape_bias && (!shape_bias_grad || pts_per_shape <= 0)) {
+        set_error("jet_backward: shape_bias given without shape_bias_grad/pts_per_shape");
+        return DIGS_EINVAL;
+    }
+    if (saved_bytes < simt::saved_bytes(net, n, want_lap)) { set_error("jet_backward: saved buffer too small"); return DIGS_ENOSPACE; }
+    size_t need = simt::bwd_ws_bytes(net, n, want_lap);
+    if (!workspace || workspace_bytes < need) {
+        set_error("jet_backward: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return DIGS_ENOSPACE;
+    }
+    return simt::jet_backward(net, xyz, n, xyz_stride, shape_bias, pts_per_shape, want_lap, f_bar, grad_bar, lap_bar,
+                              saved, workspace, grads, shape_bias ? shape_bias_grad : nullptr, (cudaStream_t)stream);
+}
+
+int digs_loss_fused(const float* f_m, const float* g_m, int64_t nm, const float* f_n, const float* g_n,
+                    const float* lap_n, int64_t nn, const float* normals, int d, const float* weights, int add_normal,
+                    int use_div, int div_l2, float div_clamp, int64_t Nm_total, int64_t Nn_total, float* fbar_m,
+                    float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n, float* terms_out, void* stream) {
+    if (!weights || !terms_out) { set_error("loss_fused: NULL weights/terms"); return DIGS_EINVAL; }
+    if (nm < 0 || nn < 0) { set_error("loss_fused: negative count"); return DIGS_EINVAL; }
+    if (nm > 0 && (!f_m || !g_m || !fbar_m || !gbar_m)) { set_error("loss_fused: NULL manifold buffer"); return DIGS_EINVAL; }
+    if (nn > 0 && (!f_n || !g_n || !fbar_n || !gbar_n)) { set_error("loss_fused: NULL non-manifold buffer"); return DIGS_EINVAL; }
+    if (use_div && nn > 0 && (!lap_n || !lbar_n)) { set_error("loss_fused: div loss without lap buffers"); return DIGS_EINVAL; }
+    if (add_normal && !normals) { set_error("loss_fused: normal term without normals"); return DIGS_EINVAL; }
+    return loss_fused(f_m, g_m, nm, f_n, g_n, lap_n, nn, normals, d, weights, add_normal, use_div, div_l2, div_clamp,
+                      Nm_total, Nn_total, fbar_m, gbar_m, fbar_n, gbar_n, lbar_n, terms_out, (cudaStream_t)stream);
+}
+
+int digs_value_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_stride, const float* shape_bias,
+                       int64_t pts_per_shape, float* f, void* workspace, size_t workspace_bytes, int mode,
+                       void* stream) {
+    int rc;
+    if ((rc = check_net(net)) || (rc = check_mode(mode))) return rc;
+    if (n < 0 || xyz_stride < net->d) { set_error("value_forward: bad n/xyz_stride"); return DIGS_EINVAL; }
+    if (n == 0) return DIGS_OK;
+    if (!xyz || !f) { set_error("value_forward: NULL buffer"); return DIGS_EINVAL; }
+    size_t need = simt::value_ws_bytes(net, n);
+    if (!workspace || workspace_bytes < need) { set_error("value_forward: workspace too small"); return DIGS_ENOSPACE; }
+    PreSrc s{};
+    s.mode = 1;
+    s.din = net->d;
+    s.xyz = xyz;
+    s.xyz_stride = xyz_stride;
+    s.W0 = net->W[0];
+    s.w0_stride = net->w0_stride;
+    s.b0 = net->b[0];
+    s.shape_bias = shape_bias;
+    s.pps = pts_per_shape > 0 ? pts_per_shape : 1;
+    return simt::value_forward(net, s, n, f, workspace, (cudaStream_t)stream);
+}
+
+int digs_grid_query(const DigsNet* net, const uint16_t* x_fp16, int nx, const uint16_t* y_fp16, int ny,
+                    const uint16_t* z_fp16, int nz, int iy_begin, int iy_end, const float* shape_bias, float* sdf_out,
+                    void* workspace, size_t workspace_bytes, int mode, void* stream) {
+    int rc;
+    if ((rc = check_net(net)) || (rc = check_mode(mode))) return rc;
+    if (net->d != 3) { set_error("grid_query: d must be 3"); return DIGS_EINVAL; }
+    if (nx <= 0 || ny <= 0 || nz <= 0 || iy_begin < 0 || iy_end > ny || iy_begin > iy_end) {
+        set_error("grid_query: bad grid extents");
+        return DIGS_EINVAL;
+    }
+    if (iy_begin == iy_end) return DIGS_OK;
+    if (!x_fp16 || !y_fp16 || !z_fp16 || !sdf_out) { set_error("grid_query: NULL buffer"); return DIGS_EINVAL; }
+    size_t need = simt::grid_ws_bytes(net);
+    if (!workspace || workspace_bytes < need) { set_error("grid_query: workspace too small"); return DIGS_ENOSPACE; }
+    return simt::grid_query(net, x_fp16, nx, y_fp16, ny, z_fp16, nz, iy_begin, iy_end, shape_bias, sdf_out, workspace,
+                            (cudaStream_t)stream);
+}
+
+}  // extern "C"

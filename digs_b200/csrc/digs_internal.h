@@ -1,0 +1,63 @@
+// Internal declarations shared by the translation units of libdigs_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/digs_b200.h"
+
+namespace digs {
+
+void set_error(const char* fmt, ...);
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Where the layer-input jets come from.
+//   mode 0: stored pre-activation planes [C][n][H] (z, Z_0..Z_{d-1}, Q)
+//   mode 1: layer 0 evaluated on the fly from point coordinates
+//   mode 2: layer 0 evaluated on the fly from grid indices + three fp16 axes
+struct PreSrc {
+    int mode;
+    int din;                  // spatial dims used by layer 0
+    const float* planes;      // mode 0
+    int64_t plane_stride;     // n*H
+    const float* xyz;         // mode 1
+    int64_t xyz_stride;
+    const float* W0;          // modes 1,2: (H, w0_stride)
+    int w0_stride;
+    const float* b0;          // (H)
+    const float* shape_bias;  // NULL or (n_shapes,H), replaces b0
+    int64_t pps;              // points per shape
+    const __half* ax;         // mode 2
+    const __half* ay;
+    const __half* az;
+    int nx, nz;
+    int64_t grid_base;        // flat index of local point 0 in [iy][ix][iz] order
+};
+
+// ---- fp32 CUDA-core path (jet_simt.cu) ------------------------------------------------------
+namespace simt {
+size_t saved_bytes(const DigsNet* net, int64_t n, int want_lap);
+size_t fwd_ws_bytes(const DigsNet* net, int64_t n, int want_lap);
+size_t bwd_ws_bytes(const DigsNet* net, int64_t n, int want_lap);
+size_t value_ws_bytes(const DigsNet* net, int64_t n);
+size_t grid_ws_bytes(const DigsNet* net);
+int jet_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_stride, const float* shape_bias,
+                int64_t pps, int want_lap, float* f, float* grad, float* lap, void* saved, void* ws,
+                cudaStream_t st);
+int jet_backward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_stride, const float* shape_bias,
+                 int64_t pps, int want_lap, const float* f_bar, const float* g_bar, const float* l_bar,
+                 const void* saved, void* ws, const DigsGrads* grads, float* shape_bias_grad, cudaStream_t st);
+int value_forward(const DigsNet* net, const PreSrc& src0, int64_t n, float* f, void* ws, cudaStream_t st);
+int grid_query(const DigsNet* net, const uint16_t* xh, int nx, const uint16_t* yh, int ny, const uint16_t* zh,
+               int nz, int iy_begin, int iy_end, const float* shape_bias, float* out, void* ws, cudaStream_t st);
+}  // namespace simt
+
+// ---- fused loss (loss_fused.cu) -------------------------------------------------------------
+int loss_fused(const float* f_m, const float* g_m, int64_t nm, const float* f_n, const float* g_n,
+               const float* lap_n, int64_t nn, const float* normals, int d, const float* weights,
+               int add_normal, int use_div, int div_l2, float div_clamp, int64_t Nm_total, int64_t Nn_total,
+               float* fbar_m, float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n, float* terms_out,
+               cudaStream_t st);
+
+}  // namespace digs

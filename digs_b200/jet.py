@@ -1,0 +1,180 @@
+"""Python operator layer over the C-ABI: forward jet / reverse pass as one torch.autograd.Function.
+
+Replaces, for one point cloud, what the reference builds out of
+  FCBlock.forward (models/DiGS.py:122-134) + utils.gradient x(1+d) (utils/utils.py:108-117,
+  models/losses.py:72-76,100-106) in the forward direction and the matching part of
+  loss.backward() (train_surface_reconstruction.py:128) in the reverse direction.
+
+PyTorch is used for device memory (caching allocator), the current stream and autograd plumbing
+only; all arithmetic happens in libdigs_b200.so.  CPU tensors are rejected: there is no fallback.
+"""
+import ctypes
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError("digs_b200: %s must be a CUDA tensor -- the hot path has no CPU fallback" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("digs_b200: %s must be float32 (got %s)" % (name, t.dtype))
+
+
+class NetSpec:
+    """Static description of the MLP (everything in DigsNet except the pointers)."""
+
+    def __init__(self, d, H, Lh, head, radius, scale, w0_stride):
+        self.d, self.H, self.Lh, self.head = int(d), int(H), int(Lh), int(head)
+        self.radius, self.scale, self.w0_stride = float(radius), float(scale), int(w0_stride)
+
+    def c_net(self, params):
+        """params: flat list [W0, b0, W1, b1, ...] of contiguous fp32 CUDA tensors."""
+        n_layers = self.Lh + 2
+        if len(params) != 2 * n_layers:
+            raise RuntimeError("digs_b200: expected %d parameter tensors, got %d" % (2 * n_layers, len(params)))
+        net = _lib.DigsNet()
+        net.d, net.H, net.Lh, net.head = self.d, self.H, self.Lh, self.head
+        net.radius, net.scale, net.w0_stride = self.radius, self.scale, self.w0_stride
+        for l in range(n_layers):
+            W, b = params[2 * l], params[2 * l + 1]
+            _require_cuda(W, "weight %d" % l)
+            _require_cuda(b, "bias %d" % l)
+            if not (W.is_contiguous() and b.is_contiguous()):
+                raise RuntimeError("digs_b200: parameters must be contiguous")
+            net.W[l] = W.data_ptr()
+            net.b[l] = b.data_ptr()
+        return net
+
+
+def _scratch(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def jet_forward_raw(spec, params, xyz, shape_bias, pts_per_shape, want_lap, save, mode):
+    """xyz (n, stride>=d) fp32 CUDA contiguous.  Returns f (n), grad (n,d), lap (n)|None, saved|None."""
+    L = _lib.lib()
+    _require_cuda(xyz, "points")
+    n, stride = xyz.shape
+    dev = xyz.device
+    net = spec.c_net(params)
+    f = torch.empty(n, dtype=torch.float32, device=dev)
+    g = torch.empty(n, spec.d, dtype=torch.float32, device=dev)
+    lap = torch.empty(n, dtype=torch.float32, device=dev) if want_lap else None
+    saved = None
+    sbytes = 0
+    if save:
+        sbytes = L.digs_saved_bytes(ctypes.byref(net), n, int(want_lap), mode)
+        saved = _scratch(sbytes, dev)
+    wbytes = L.digs_forward_workspace_bytes(ctypes.byref(net), n, int(want_lap), mode)
+    if n > 0 and wbytes == 0:
+        _lib.check(-1, "forward_workspace_bytes")
+    ws = _scratch(wbytes, dev)
+    rc = L.digs_jet_forward(ctypes.byref(net), _ptr(xyz), n, stride, _ptr(shape_bias), int(pts_per_shape),
+                            int(want_lap), _ptr(f), _ptr(g), _ptr(lap), _ptr(saved), sbytes, _ptr(ws), wbytes,
+                            mode, _stream())
+    _lib.check(rc, "jet_forward")
+    return f, g, lap, saved
+
+
+def jet_backward_raw(spec, params, xyz, shape_bias, pts_per_shape, want_lap, f_bar, g_bar, l_bar, saved, mode,
+                     grad_out=None):
+    """Returns (list of parameter gradients aligned with params, shape_bias_grad|None).
+
+    grad_out: optional list of preallocated fp32 tensors to ACCUMULATE into (flat-buffer views)."""
+    L = _lib.lib()
+    n, stride = xyz.shape
+    dev = xyz.device
+    net = spec.c_net(params)
+    if grad_out is None:
+        grad_out = [torch.zeros_like(p) for p in params]
+    gr = _lib.DigsGrads()
+    for l in range(spec.Lh + 2):
+        gr.dW[l] = grad_out[2 * l].data_ptr()
+        gr.db[l] = grad_out[2 * l + 1].data_ptr()
+    sb_grad = torch.zeros_like(shape_bias) if shape_bias is not None else None
+    wbytes = L.digs_backward_workspace_bytes(ctypes.byref(net), n, int(want_lap), mode)
+    ws = _scratch(wbytes, dev)
+    for t in (f_bar, g_bar, l_bar):
+        if t is not None:
+            _require_cuda(t, "adjoint seed")
+    rc = L.digs_jet_backward(ctypes.byref(net), _ptr(xyz), n, stride, _ptr(shape_bias), int(pts_per_shape),
+                             int(want_lap), _ptr(f_bar), _ptr(g_bar), _ptr(l_bar), _ptr(saved), saved.numel(),
+                             _ptr(ws), wbytes, ctypes.byref(gr), _ptr(sb_grad), mode, _stream())
+    _lib.check(rc, "jet_backward")
+    return grad_out, sb_grad
+
+
+def value_forward_raw(spec, params, xyz, shape_bias, pts_per_shape, mode):
+    L = _lib.lib()
+    _require_cuda(xyz, "points")
+    n, stride = xyz.shape
+    net = spec.c_net(params)
+    f = torch.empty(n, dtype=torch.float32, device=xyz.device)
+    wbytes = L.digs_value_workspace_bytes(ctypes.byref(net), n, mode)
+    ws = _scratch(wbytes, xyz.device)
+    rc = L.digs_value_forward(ctypes.byref(net), _ptr(xyz), n, stride, _ptr(shape_bias), int(pts_per_shape),
+                              _ptr(f), _ptr(ws), wbytes, mode, _stream())
+    _lib.check(rc, "value_forward")
+    return f
+
+
+class JetFunction(torch.autograd.Function):
+    """(f, grad f, lap f) = jet(points; params); differentiable once w.r.t. params and shape_bias.
+
+    The gradient w.r.t. the points themselves is provided at first order only (f_bar * grad f); asking
+    for it while grad/lap outputs also carry adjoints would need Hessian-vector products and raises.
+    """
+
+    @staticmethod
+    def forward(ctx, xyz, shape_bias, spec, pts_per_shape, want_lap, mode, *params):
+        params = [p.detach() for p in params]
+        xyz_d = xyz.detach()
+        sb = None if shape_bias is None else shape_bias.detach().contiguous()
+        f, g, lap, saved = jet_forward_raw(spec, params, xyz_d, sb, pts_per_shape, want_lap, True, mode)
+        ctx.spec, ctx.pps, ctx.want_lap, ctx.mode = spec, pts_per_shape, want_lap, mode
+        ctx.has_sb = sb is not None
+        ctx.save_for_backward(xyz_d, g, saved, *( [sb] if sb is not None else [] ), *params)
+        ctx.set_materialize_grads(False)
+        if lap is None:
+            lap = torch.empty(0, dtype=torch.float32, device=xyz.device)
+            ctx.mark_non_differentiable(lap)
+        return f, g, lap
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, f_bar, g_bar, l_bar):
+        tensors = ctx.saved_tensors
+        xyz, g, saved = tensors[0], tensors[1], tensors[2]
+        k = 3
+        sb = None
+        if ctx.has_sb:
+            sb = tensors[3]
+            k = 4
+        params = list(tensors[k:])
+        if not ctx.want_lap:
+            l_bar = None
+        fb = None if f_bar is None else f_bar.contiguous()
+        gb = None if g_bar is None else g_bar.contiguous()
+        lb = None if l_bar is None else l_bar.contiguous()
+        grads, sb_grad = jet_backward_raw(ctx.spec, params, xyz, sb, ctx.pps, ctx.want_lap, fb, gb, lb, saved,
+                                          ctx.mode)
+        xyz_grad = None
+        if ctx.needs_input_grad[0]:
+            if gb is not None or lb is not None:
+                raise RuntimeError(
+                    "digs_b200: gradient w.r.t. the points through grad/lap outputs needs second-order "
+                    "point derivatives, which the fused jet does not provide (SURVEY 8b limit); use the "
+                    "reference autograd path for that caller")
+            xyz_grad = torch.zeros_like(xyz)
+            if fb is not None:
+                xyz_grad[:, :ctx.spec.d] = fb[:, None] * g
+        return (xyz_grad, sb_grad, None, None, None, None, *grads)

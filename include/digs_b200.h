@@ -1,0 +1,142 @@
+/*
+ * digs_b200.h -- C-ABI of libdigs_b200.so: the B200-native DiGS hot path.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream (as void*); there are no
+ * torch types in any signature.  All buffers are BORROWED for the duration of the call and are
+ * stream-ordered: the library never allocates or frees caller memory, never synchronises the
+ * host, and is CUDA-graph capturable.  Return value: 0 on success, a negative DIGS_E* code on
+ * failure, with a thread-local message available from digs_last_error().
+ *
+ * Reference interfaces replaced (paths relative to the DiGS repository):
+ *   digs_jet_forward      FCBlock.forward (models/DiGS.py:122-134) applied to a point cloud, PLUS the
+ *                         utils.gradient calls DiGSLoss makes on its output: first order
+ *                         (models/losses.py:72,76; utils/utils.py:108-117) and the per-axis second
+ *                         pass whose trace is the divergence (models/losses.py:100-106).
+ *   digs_jet_backward     the part of loss.backward() (train_surface_reconstruction.py:128,
+ *                         train_basic_shape.py:132, train_shapespace.py:145) that runs from
+ *                         (dL/df, dL/dgrad f, dL/dlap f) down to the 2(Lh+2) parameter gradients.
+ *   digs_loss_fused       DiGSLoss.forward's term evaluation (models/losses.py:107-184) and the
+ *                         adjoint seeds autograd would derive from it.
+ *   digs_value_forward    decoder(points) under no_grad (utils/utils.py:348,
+ *                         compute_metrics_shapenet.py:134).
+ *   digs_grid_query       the chunk loop of utils.implicit2mesh (utils/utils.py:343-350) over the
+ *                         grid of utils.get_3d_grid (utils/utils.py:186-215), coordinates
+ *                         generated on the device from the three fp16-rounded axes.
+ *
+ * Channel convention ("jet"): per point the kernels carry the value h, d Jacobian columns A_k and
+ * (optionally) the Laplacian P through every layer: C = 1 + d + want_lap channels.
+ */
+#ifndef DIGS_B200_H_
+#define DIGS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIGS_ABI_VERSION 1
+#define DIGS_MAX_LAYERS 18 /* Lh + 2 <= 18 */
+
+/* error codes */
+#define DIGS_OK 0
+#define DIGS_EINVAL (-1)  /* bad argument / unsupported configuration */
+#define DIGS_ENOSPACE (-2) /* caller-provided workspace too small */
+#define DIGS_ECUDA (-3)    /* CUDA runtime error at launch */
+#define DIGS_ENOTIMPL (-4) /* precision mode not available for this configuration */
+
+/* precision modes */
+#define DIGS_MODE_FP32 0      /* CUDA-core fp32 FMAs, fp32 accumulate (reference-grade) */
+#define DIGS_MODE_BF16X2 1    /* tcgen05 tensor cores, bf16 hi+lo split operands, 3 MMA passes */
+#define DIGS_MODE_BF16 2      /* tcgen05 tensor cores, single-pass bf16 operands (stated looser bound) */
+
+/* output head (models/DiGS.py:128-132) */
+#define DIGS_HEAD_IDENTITY 0 /* init_type siren: f = u */
+#define DIGS_HEAD_SQRT 1     /* init_type mfgi / geometric_sine: f = scale*(sign(u)sqrt(|u|+1e-8) - radius) */
+
+/* Network description: nn.Linear layout, weight (out,in) row-major fp32, exactly the tensors
+ * named decoder.fc_block.net.{i}.0.{weight,bias} (models/DiGS.py:88-99). */
+typedef struct DigsNet {
+    int32_t d;         /* spatial input dims: 2 or 3 */
+    int32_t H;         /* hidden width, multiple of 64, <= 1024 */
+    int32_t Lh;        /* number of HxH layers (decoder_n_hidden_layers), >= 1 */
+    int32_t head;      /* DIGS_HEAD_* */
+    float radius;      /* sphere_init_params[0] */
+    float scale;       /* sphere_init_params[1] */
+    int32_t w0_stride; /* row stride (floats) of W[0]: d + latent_size */
+    int32_t reserved;
+    const float* W[DIGS_MAX_LAYERS]; /* W[0] (H,w0_stride); W[1..Lh] (H,H); W[Lh+1] (1,H) */
+    const float* b[DIGS_MAX_LAYERS]; /* b[0..Lh] (H); b[Lh+1] (1) */
+} DigsNet;
+
+/* Gradient destinations, same indexing as DigsNet.W/b.  Kernels ACCUMULATE (+=) into them.
+ * Only the first d columns of dW[0] rows are written (latent columns are handled by the caller
+ * through shape_bias_grad). */
+typedef struct DigsGrads {
+    float* dW[DIGS_MAX_LAYERS];
+    float* db[DIGS_MAX_LAYERS];
+} DigsGrads;
+
+int digs_abi_version(void);
+const char* digs_last_error(void);
+
+/* Bytes of the `saved` buffer digs_jet_forward fills for digs_jet_backward (0 if no backward wanted). */
+size_t digs_saved_bytes(const DigsNet* net, int64_t n, int want_lap, int precision_mode);
+/* Bytes of scratch digs_jet_forward / digs_jet_backward / digs_value_forward / digs_grid_query need. */
+size_t digs_forward_workspace_bytes(const DigsNet* net, int64_t n, int want_lap, int precision_mode);
+size_t digs_backward_workspace_bytes(const DigsNet* net, int64_t n, int want_lap, int precision_mode);
+size_t digs_value_workspace_bytes(const DigsNet* net, int64_t n, int precision_mode);
+size_t digs_grid_workspace_bytes(const DigsNet* net, int precision_mode);
+
+/* Forward jet of one point cloud.
+ *  xyz          (n, xyz_stride) fp32, the first d columns are the coordinates.
+ *  shape_bias   NULL, or (n_shapes, H): per-shape replacement for b[0] (= W0[:,d:] latent + b0,
+ *               SURVEY 8a); point i belongs to shape i / pts_per_shape.
+ *  f (n), grad (n,d), lap (n or NULL when !want_lap): outputs.
+ *  saved        NULL (inference) or digs_saved_bytes() bytes. */
+int digs_jet_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_stride,
+                     const float* shape_bias, int64_t pts_per_shape, int want_lap,
+                     float* f, float* grad, float* lap,
+                     void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes,
+                     int precision_mode, void* stream);
+
+/* Reverse pass.  f_bar (n), grad_bar (n,d), lap_bar (n or NULL): adjoint seeds.
+ * Accumulates into grads->dW/db; shape_bias_grad (n_shapes,H) or NULL, accumulated. */
+int digs_jet_backward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_stride,
+                      const float* shape_bias, int64_t pts_per_shape, int want_lap,
+                      const float* f_bar, const float* grad_bar, const float* lap_bar,
+                      const void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes,
+                      const DigsGrads* grads, float* shape_bias_grad,
+                      int precision_mode, void* stream);
+
+/* Loss terms + adjoint seeds in one launch (in-scope loss types; SURVEY 8a "adjoint seeds").
+ *  weights[6] = {sdf, inter, normal, eikonal, div, latent}; add_normal: loss type adds the normal
+ *  term; use_div: loss type has 'div'; div_l2: 0 = l1, 1 = l2; normals may be NULL.
+ *  Nm_total / Nn_total: GLOBAL point counts the means are taken over (>= local n when sharded).
+ *  terms_out[8] (device): loss(partial, without latent term), sdf, inter, eikonal, normal, div, 0, 0
+ *  -- accumulated with atomics, caller zeroes them first. */
+int digs_loss_fused(const float* f_m, const float* g_m, int64_t nm, const float* f_n, const float* g_n,
+                    const float* lap_n, int64_t nn, const float* normals, int d,
+                    const float* weights, int add_normal, int use_div, int div_l2, float div_clamp,
+                    int64_t Nm_total, int64_t Nn_total,
+                    float* fbar_m, float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n,
+                    float* terms_out, void* stream);
+
+/* decoder(points) -> (n) values, no derivative channels, nothing saved. */
+int digs_value_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_stride,
+                       const float* shape_bias, int64_t pts_per_shape, float* f,
+                       void* workspace, size_t workspace_bytes, int precision_mode, void* stream);
+
+/* Dense grid query.  Axes are IEEE fp16 bit patterns (utils/utils.py:208-211 rounds the grid to
+ * fp16).  Flat output order is [iy][ix][iz] (np.meshgrid indexing='xy', utils/utils.py:208,349);
+ * this call writes rows iy in [iy_begin, iy_end) to sdf_out + (iy - iy_begin)*nx*nz. */
+int digs_grid_query(const DigsNet* net, const uint16_t* x_fp16, int nx, const uint16_t* y_fp16, int ny,
+                    const uint16_t* z_fp16, int nz, int iy_begin, int iy_end,
+                    const float* shape_bias, float* sdf_out,
+                    void* workspace, size_t workspace_bytes, int precision_mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIGS_B200_H_ */

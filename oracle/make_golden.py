@@ -1,0 +1,200 @@
+"""TEST INFRASTRUCTURE ONLY.  Generate tests/golden/*.npz by RUNNING THE REAL REFERENCE (/root/reference).
+
+Run in the build container (the reference tree does not exist on the GPU box):
+
+    python -m oracle.make_golden
+
+Everything written here is an output of the unmodified reference modules models/DiGS.py,
+models/losses.py and utils/utils.py (imported with five stub modules, oracle/reference_loader.py):
+  * init_*      sha256 of every parameter tensor after seeded construction (all three init schemes)
+  * step_*      jets (f, grad f, lap f), the 8 loss terms and all parameter gradients of one
+                forward + DiGSLoss + backward, in fp64 (ground truth) and fp32 (the reference's own noise floor)
+  * grid_*      get_3d_grid axes and decoder values in the reference's flat point order
+  * divw_*      update_div_weight schedules
+"""
+import copy
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import reference_loader  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+# name -> dict(net kwargs, loss kwargs, Nm, Nn, bs, seed)
+STEP_CASES = {
+    "c2_small": dict(net=dict(latent_size=0, in_dim=3, decoder_hidden_dim=256, nl="sine", encoder_type="none",
+                              decoder_n_hidden_layers=4, init_type="mfgi", sphere_init_params=[1.6, 0.1]),
+                     loss=dict(weights=[3e3, 1e2, 1e2, 5e1, 1e2], loss_type="siren_wo_n_w_div", div_decay="linear",
+                               div_type="l1", div_clamp=50), Nm=512, Nn=512, bs=1, seed=3627473, box=1.1),
+    "c1_small": dict(net=dict(latent_size=0, in_dim=2, decoder_hidden_dim=128, nl="sine", encoder_type="none",
+                              decoder_n_hidden_layers=4, init_type="mfgi"),
+                     loss=dict(weights=[3e3, 1e2, 1e2, 5e1, 1e2], loss_type="siren_wo_n_w_div", div_decay="linear",
+                               div_type="l1", div_clamp=50), Nm=384, Nn=384, bs=1, seed=11, box=1.2),
+    "siren_l2_ragged": dict(net=dict(latent_size=0, in_dim=3, decoder_hidden_dim=128, nl="sine", encoder_type="none",
+                                     decoder_n_hidden_layers=2, init_type="siren"),
+                            loss=dict(weights=[3e3, 1e2, 1e2, 5e1, 1e1], loss_type="siren_w_div", div_decay="none",
+                                      div_type="l2", div_clamp=50), Nm=301, Nn=203, bs=1, seed=5, box=1.1),
+    "geo_siren_loss": dict(net=dict(latent_size=0, in_dim=3, decoder_hidden_dim=64, nl="sine", encoder_type="none",
+                                    decoder_n_hidden_layers=3, init_type="geometric_sine",
+                                    sphere_init_params=[1.6, 1.0]),
+                           loss=dict(weights=[3e3, 1e2, 1e2, 5e1, 1e2], loss_type="siren", div_decay="none",
+                                     div_type="l1", div_clamp=50), Nm=130, Nn=130, bs=2, seed=7, box=1.1),
+    "wo_n_2d": dict(net=dict(latent_size=0, in_dim=2, decoder_hidden_dim=64, nl="sine", encoder_type="none",
+                             decoder_n_hidden_layers=1, init_type="siren"),
+                    loss=dict(weights=[3e3, 1e2, 1e2, 5e1, 1e2], loss_type="siren_wo_n", div_decay="none",
+                              div_type="l1", div_clamp=50), Nm=64, Nn=96, bs=1, seed=9, box=1.2),
+    "latent_small": dict(net=dict(latent_size=16, in_dim=3, decoder_hidden_dim=128, nl="sine",
+                                  encoder_type="autodecoder", decoder_n_hidden_layers=2, init_type="mfgi",
+                                  sphere_init_params=[1.6, 0.1]),
+                         loss=dict(weights=[3e3, 1e2, 1e2, 5e1, 1e2, 1e0], loss_type="siren_wo_n_w_div",
+                                   div_decay="linear", div_type="l1", div_clamp=50), Nm=96, Nn=96, bs=2, seed=13,
+                         box=1.2),
+}
+
+INIT_CASES = {
+    "mfgi_c2": dict(latent_size=0, in_dim=3, decoder_hidden_dim=256, nl="sine", encoder_type="none",
+                    decoder_n_hidden_layers=4, init_type="mfgi", sphere_init_params=[1.6, 0.1]),
+    "mfgi_c1": dict(latent_size=0, in_dim=2, decoder_hidden_dim=128, nl="sine", encoder_type="none",
+                    decoder_n_hidden_layers=4, init_type="mfgi"),
+    "siren_c4": dict(latent_size=0, in_dim=3, decoder_hidden_dim=512, nl="sine", encoder_type="none",
+                     decoder_n_hidden_layers=8, init_type="siren"),
+    "geo": dict(latent_size=0, in_dim=3, decoder_hidden_dim=64, nl="sine", encoder_type="none",
+                decoder_n_hidden_layers=3, init_type="geometric_sine"),
+    "mfgi_c5": dict(latent_size=256, in_dim=3, decoder_hidden_dim=256, nl="sine", encoder_type="autodecoder",
+                    decoder_n_hidden_layers=8, init_type="mfgi", sphere_init_params=[1.6, 0.1]),
+}
+INIT_SEED = 3627473
+
+
+def sha(t):
+    return hashlib.sha256(t.detach().cpu().contiguous().numpy().tobytes()).hexdigest()
+
+
+def make_inputs(case, dtype):
+    """Deterministic synthetic clouds: manifold on a sphere/circle r=0.5 (+ analytic normals), off-surface uniform."""
+    rng = np.random.RandomState(case["seed"])
+    d = case["net"]["in_dim"]
+    bs, Nm, Nn = case["bs"], case["Nm"], case["Nn"]
+    v = rng.normal(size=(bs, Nm, d))
+    v /= np.linalg.norm(v, axis=-1, keepdims=True)
+    m = (0.5 * v).astype(np.float32)
+    nrm = v.astype(np.float32)
+    nm = rng.uniform(-case["box"], case["box"], size=(bs, Nn, d)).astype(np.float32)
+    lat = None
+    if case["net"]["latent_size"] > 0:
+        lat = (0.01 * rng.normal(size=(bs, case["net"]["latent_size"]))).astype(np.float32)
+    return m, nrm, nm, lat
+
+
+def run_reference_step(ref_digs, case, dtype):
+    torch.manual_seed(case["seed"])
+    net = ref_digs.DiGSNetwork(**case["net"])
+    crit = ref_digs.DiGSLoss(**copy.deepcopy(case["loss"]))
+    m, nrm, nm, lat = make_inputs(case, dtype)
+    net = net.to(dtype)
+    m_t, n_t, nm_t = (torch.tensor(a, dtype=dtype) for a in (m, nrm, nm))
+    m_t.requires_grad_()
+    nm_t.requires_grad_()
+    lat_t = None
+    if lat is not None:
+        lat_t = torch.tensor(lat, dtype=dtype, requires_grad=True)
+        m_in = torch.cat([m_t, lat_t[:, None, :].expand(-1, m_t.shape[1], -1)], dim=-1)
+        nm_in = torch.cat([nm_t, lat_t[:, None, :].expand(-1, nm_t.shape[1], -1)], dim=-1)
+    else:
+        m_in, nm_in = m_t, nm_t
+    out = net(nm_in, m_in)
+    loss_dict, mnfld_grad = crit(out, m_t, nm_t, n_t)
+    # jets as the loss sees them (utils/utils.py:108-117, models/losses.py:72-106)
+    import utils.utils as U
+    g_n = U.gradient(nm_t, out["nonmanifold_pnts_pred"])
+    d = m_t.shape[-1]
+    lap = sum(U.gradient(nm_t, g_n[:, :, k])[:, :, k] for k in range(d))
+    loss_dict["loss"].backward()
+    res = dict(f_m=out["manifold_pnts_pred"], g_m=mnfld_grad, f_n=out["nonmanifold_pnts_pred"], g_n=g_n, lap_n=lap)
+    res = {k: v.detach().numpy() for k, v in res.items()}
+    for k, v in loss_dict.items():
+        res["term_" + k] = np.asarray(v.detach().numpy()).reshape(-1)[:1]
+    for name, p in net.named_parameters():
+        res["grad_" + name] = p.grad.detach().numpy()
+    if lat_t is not None:
+        res["grad_latent"] = lat_t.grad.detach().numpy()
+    shas = {name: sha(p.float()) for name, p in net.named_parameters()}
+    return res, shas, (m, nrm, nm, lat)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref_digs, ref_losses, ref_utils = reference_loader.load()
+
+    # ---- init fingerprints -----------------------------------------------------------------------
+    init = {}
+    for name, kw in INIT_CASES.items():
+        torch.manual_seed(INIT_SEED)
+        net = ref_digs.DiGSNetwork(**kw)
+        for pname, p in net.named_parameters():
+            init["%s/%s" % (name, pname)] = np.array(sha(p))
+            init["%s/%s/head" % (name, pname)] = p.detach().reshape(-1)[:8].numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "init_fingerprints.npz"), **init)
+
+    # ---- step fixtures -----------------------------------------------------------------------------
+    for name, case in STEP_CASES.items():
+        r64, shas, (m, nrm, nm, lat) = run_reference_step(ref_digs, case, torch.float64)
+        r32, shas32, _ = run_reference_step(ref_digs, case, torch.float32)
+        blob = dict(in_mnfld=m, in_normals=nrm, in_nonmnfld=nm)
+        if lat is not None:
+            blob["in_latent"] = lat
+        for k, v in r64.items():
+            # jets/terms in fp64; the (large) parameter gradients rounded to fp32 -- tolerance in tests is 1e-4
+            blob["ref64_" + k] = v.astype(np.float32) if k.startswith("grad_") else v
+        for k, v in r32.items():
+            if not k.startswith("grad_"):
+                blob["ref32_" + k] = v
+        for k, v in shas32.items():
+            blob["sha_" + k] = np.array(v)
+        np.savez_compressed(os.path.join(OUT, "step_%s.npz" % name), **blob)
+        print("step", name, {k: float(v[0]) for k, v in r64.items() if k.startswith("term_")})
+
+    # ---- grid fixtures -----------------------------------------------------------------------------
+    grid = {}
+    for tag, (res, bbox) in {"cube16": (16, np.array([[-1, 1], [-1, 1], [-1, 1]], dtype=float)),
+                             "box20": (20, np.array([[-0.9, 0.8], [-0.5, 0.45], [-0.7, 0.75]])),
+                             "zshort12": (12, np.array([[-1.0, 1.0], [-0.8, 0.9], [-0.3, 0.3]]))}.items():
+        gd = ref_utils.get_3d_grid(resolution=res, bbox=bbox)
+        for a, ax in zip("xyz", gd["xyz"]):
+            grid["%s/%s" % (tag, a)] = ax
+        grid["%s/bbox" % tag] = bbox
+        grid["%s/res" % tag] = np.array(res)
+        grid["%s/points_f16" % tag] = gd["grid_points"].numpy()
+        torch.manual_seed(INIT_SEED)
+        net = ref_digs.DiGSNetwork(latent_size=0, in_dim=3, decoder_hidden_dim=64, nl="sine", encoder_type="none",
+                                   decoder_n_hidden_layers=2, init_type="mfgi", sphere_init_params=[1.6, 0.1])
+        with torch.no_grad():
+            grid["%s/values32" % tag] = net.decoder(gd["grid_points"].float()).numpy()[:, 0]
+            grid["%s/values64" % tag] = net.double().decoder(gd["grid_points"].double()).numpy()[:, 0]
+    np.savez_compressed(os.path.join(OUT, "grid.npz"), **grid)
+
+    # ---- div-weight schedules ----------------------------------------------------------------------
+    sched = {}
+    for decay in ("linear", "quintic", "step", "none"):
+        for pname, params in {"recipe": (1e2, 0.2, 1e2, 0.4, 0.0, 0.0), "scene": (1e1, 0.1, 1e1, 0.3, 0.0, 0.0),
+                              "two": (50.0, 5.0)}.items():
+            crit = ref_digs.DiGSLoss(weights=[3e3, 1e2, 1e2, 5e1, 1e2], loss_type="siren_wo_n_w_div",
+                                     div_decay=decay, div_type="l1")
+            vals = []
+            for it in range(0, 1001, 25):
+                crit.update_div_weight(it, 1000, params)
+                vals.append(crit.weights[4])
+            sched["%s/%s" % (decay, pname)] = np.array(vals, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "div_weight.npz"), **sched)
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
