@@ -37,7 +37,7 @@ class DigsGrads(ctypes.Structure):
 
 
 EXPORTS = (
-    "digs_abi_version", "digs_last_error", "digs_saved_bytes", "digs_forward_workspace_bytes",
+    "digs_abi_version", "digs_last_error", "digs_launch_count", "digs_saved_bytes", "digs_forward_workspace_bytes",
     "digs_backward_workspace_bytes", "digs_value_workspace_bytes", "digs_grid_workspace_bytes",
     "digs_jet_forward", "digs_jet_backward", "digs_loss_fused", "digs_value_forward", "digs_grid_query",
 )
@@ -59,6 +59,7 @@ def lib():
     netp = ctypes.POINTER(DigsNet)
     L.digs_abi_version.restype = i32
     L.digs_last_error.restype = ctypes.c_char_p
+    L.digs_launch_count.restype = ctypes.c_longlong
     L.digs_saved_bytes.restype = sz
     L.digs_saved_bytes.argtypes = [netp, i64, i32, i32]
     L.digs_forward_workspace_bytes.restype = sz

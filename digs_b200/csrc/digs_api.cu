@@ -2,9 +2,12 @@
 #include "digs_internal.h"
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 
 namespace digs {
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -46,6 +49,7 @@ extern "C" {
 
 int digs_abi_version(void) { return DIGS_ABI_VERSION; }
 const char* digs_last_error(void) { return g_err; }
+long long digs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 size_t digs_saved_bytes(const DigsNet* net, int64_t n, int want_lap, int mode) {
     if (check_net(net) || check_mode(mode) || n < 0) return 0;

@@ -9,6 +9,7 @@
 namespace digs {
 
 void set_error(const char* fmt, ...);
+void count_launch(int n = 1);  // process-wide count of kernels launched by this library
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -609,7 +609,7 @@ static int launch_transpose(const DigsNet* net, float* Wt, cudaStream_t st) {
     WPtrs wp;
     for (int l = 0; l < net->Lh; ++l) wp.w[l] = net->W[1 + l];
     dim3 g(net->H / 32, net->H / 32, net->Lh), b(32, 8);
-    k_transpose<<<g, b, 0, st>>>(wp, Wt, net->H);
+    k_transpose<<<g, b, 0, st>>>(wp, Wt, net->H); count_launch();
     return 0;
 }
 
@@ -648,18 +648,18 @@ static int forward_t(const DigsNet* net, const PreSrc& src0, int64_t n, float* f
         float* outp = planes + (pingpong ? ((l & 1) ? 0 : align_up(plane_set * 4, 256) / 4) : (size_t)(l - 1) * plane_set);
         const float* Wl = Wt + (size_t)(l - 1) * H * H;
         if (l == 1) {
-            k_hidden_fwd<D, LAP, true><<<grid, NTHREADS, 0, st>>>(src0, Wl, net->b[l], outp, n, H);
+            k_hidden_fwd<D, LAP, true><<<grid, NTHREADS, 0, st>>>(src0, Wl, net->b[l], outp, n, H); count_launch();
         } else {
             float* inp = planes + (pingpong ? (((l - 1) & 1) ? 0 : align_up(plane_set * 4, 256) / 4)
                                             : (size_t)(l - 2) * plane_set);
-            k_hidden_fwd<D, LAP, false><<<grid, NTHREADS, 0, st>>>(make_plane_src(inp, n, H), Wl, net->b[l], outp, n, H);
+            k_hidden_fwd<D, LAP, false><<<grid, NTHREADS, 0, st>>>(make_plane_src(inp, n, H), Wl, net->b[l], outp, n, H); count_launch();
         }
     }
     int L = net->Lh;
     float* lastp = planes + (pingpong ? ((L & 1) ? 0 : align_up(plane_set * 4, 256) / 4) : (size_t)(L - 1) * plane_set);
     unsigned hb = (unsigned)((n + 7) / 8);
     k_head_fwd<D, LAP, false><<<hb, 256, 0, st>>>(make_plane_src(lastp, n, H), net->W[L + 1], net->b[L + 1], net->head,
-                                                  net->radius, net->scale, f, grad, lap, head_saved, n, H);
+                                                  net->radius, net->scale, f, grad, lap, head_saved, n, H); count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("simt forward launch: %s", cudaGetErrorString(e)); return DIGS_ECUDA; }
     return DIGS_OK;
@@ -742,13 +742,13 @@ static int backward_t(const DigsNet* net, const PreSrc& src0, int64_t n, const f
     float* ubar = ws + 3 * plane_al;
 
     k_head_seed<D, LAP><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(head_saved, f_bar, g_bar, l_bar, net->head,
-                                                                      net->scale, ubar, gr->db[L + 1], n);
+                                                                      net->scale, ubar, gr->db[L + 1], n); count_launch();
     {
         const int ppb = 64;
         int bt = H < 256 ? H : 256;
         dim3 g(H / bt, (unsigned)((n + ppb - 1) / ppb));
         k_head_wgrad<D, LAP, false><<<g, bt, ppb * C * sizeof(float), st>>>(
-            make_plane_src(saved_planes + (size_t)(L - 1) * plane_set, n, H), ubar, gr->dW[L + 1], n, H, ppb);
+            make_plane_src(saved_planes + (size_t)(L - 1) * plane_set, n, H), ubar, gr->dW[L + 1], n, H, ppb); count_launch();
     }
     dim3 grid((unsigned)((n + G::TP - 1) / G::TP), H / TN);
     int nsplit = (int)((n + 1023) / 1024);
@@ -760,28 +760,31 @@ static int backward_t(const DigsNet* net, const PreSrc& src0, int64_t n, const f
     for (int l = L; l >= 1; --l) {
         PreSrc pre = make_plane_src(saved_planes + (size_t)(l - 1) * plane_set, n, H);
         float* outp = inc[l & 1];
-        if (l == L)
+        if (l == L) {
             k_hidden_bwd<D, LAP, true><<<grid, NTHREADS, 0, st>>>(pre, nullptr, ubar, net->W[L + 1], net->W[l], Gbuf,
                                                                   outp, n, H, 1);
-        else
+        } else {
             k_hidden_bwd<D, LAP, false><<<grid, NTHREADS, 0, st>>>(pre, inc[(l + 1) & 1], nullptr, nullptr, net->W[l],
                                                                    Gbuf, outp, n, H, 1);
-        if (l == 1)
+        }
+        if (l == 1) {
             k_wgrad<D, LAP, true><<<wgrid, NTHREADS, 0, st>>>(src0, Gbuf, gr->dW[l], n, H, pps_split);
-        else
+        } else {
             k_wgrad<D, LAP, false><<<wgrid, NTHREADS, 0, st>>>(
                 make_plane_src(saved_planes + (size_t)(l - 2) * plane_set, n, H), Gbuf, gr->dW[l], n, H, pps_split);
+        }
+        count_launch(2);
         {
             int bt = H < 256 ? H : 256;
             dim3 g(H / bt, (unsigned)((n + 255) / 256));
-            k_colsum<<<g, bt, 0, st>>>(Gbuf, gr->db[l], n, H, 256);
+            k_colsum<<<g, bt, 0, st>>>(Gbuf, gr->db[l], n, H, 256); count_launch();
         }
     }
     {
         int bt = H < 128 ? H : 128;
         const int ppb = 128;
         dim3 g(H / bt, (unsigned)((n + ppb - 1) / ppb));
-        k_layer0_bwd<D, LAP><<<g, bt, 0, st>>>(src0, inc[1], gr->dW[0], net->w0_stride, gr->db[0], sb_grad, n, H, ppb);
+        k_layer0_bwd<D, LAP><<<g, bt, 0, st>>>(src0, inc[1], gr->dW[0], net->w0_stride, gr->db[0], sb_grad, n, H, ppb); count_launch();
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("simt backward launch: %s", cudaGetErrorString(e)); return DIGS_ECUDA; }

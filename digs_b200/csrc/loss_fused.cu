@@ -129,9 +129,10 @@ int loss_fused(const float* f_m, const float* g_m, int64_t nm, const float* f_n,
     int64_t m = nm > nn ? nm : nn;
     if (m == 0) return DIGS_OK;
     unsigned blocks = (unsigned)((m + 255) / 256);
-    if (d == 3) k_loss<3><<<blocks, 256, 0, st>>>(a);
-    else if (d == 2) k_loss<2><<<blocks, 256, 0, st>>>(a);
+    if (d == 3) { k_loss<3><<<blocks, 256, 0, st>>>(a); }
+    else if (d == 2) { k_loss<2><<<blocks, 256, 0, st>>>(a); }
     else { set_error("loss_fused: d must be 2 or 3"); return DIGS_EINVAL; }
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("loss_fused launch: %s", cudaGetErrorString(e)); return DIGS_ECUDA; }
     return DIGS_OK;

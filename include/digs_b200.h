@@ -80,6 +80,8 @@ typedef struct DigsGrads {
 
 int digs_abi_version(void);
 const char* digs_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (for bench.py's gpu_launches). */
+long long digs_launch_count(void);
 
 /* Bytes of the `saved` buffer digs_jet_forward fills for digs_jet_backward (0 if no backward wanted). */
 size_t digs_saved_bytes(const DigsNet* net, int64_t n, int want_lap, int precision_mode);

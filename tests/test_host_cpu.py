@@ -1,0 +1,184 @@
+"""CPU: host-side logic of the drop-in layer and the C-ABI surface (no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import digs_b200
+from digs_b200 import _lib, dist as ddist
+from digs_b200.grid import grid_axes, slab_range
+from oracle.make_golden import INIT_CASES, INIT_SEED
+from _util import golden, sha, build_net
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = _lib.lib()
+    assert L.digs_abi_version() == 1
+    header = open(os.path.join(ROOT, "include", "digs_b200.h")).read()
+    declared = set(re.findall(r"\b(digs_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no entry points found in the header"
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_library_rejects_bad_arguments_without_a_gpu():
+    L = _lib.lib()
+    net = _lib.DigsNet()
+    net.d, net.H, net.Lh, net.head = 5, 256, 4, 0
+    assert L.digs_saved_bytes(ctypes.byref(net), 10, 1, 0) == 0
+    assert b"net.d" in L.digs_last_error()
+    rc = L.digs_jet_forward(ctypes.byref(net), None, 10, 3, None, 0, 1, None, None, None, None, 0, None, 0, 0, None)
+    assert rc == -1
+    net.d = 3
+    for l in range(6):
+        net.W[l] = 256
+        net.b[l] = 256
+    net.w0_stride = 3
+    # tensor-core modes are explicit: never a silent fallback
+    assert L.digs_saved_bytes(ctypes.byref(net), 10, 1, 7) == 0
+    assert L.digs_saved_bytes(ctypes.byref(net), 1000, 1, 0) >= 4 * 5 * 1000 * 256 * 4
+
+
+@pytest.mark.parametrize("name", sorted(INIT_CASES))
+def test_init_bitwise_equal_to_reference(name):
+    g = golden("init_fingerprints.npz")
+    net = build_net(INIT_CASES[name], INIT_SEED)
+    keys = [k for k in g.files if k.startswith(name + "/") and not k.endswith("/head")]
+    assert len(keys) == len(list(net.named_parameters()))
+    for pname, p in net.named_parameters():
+        assert sha(p) == str(g["%s/%s" % (name, pname)]), pname
+        np.testing.assert_array_equal(p.detach().reshape(-1)[:8].numpy(), g["%s/%s/head" % (name, pname)])
+
+
+def test_state_dict_keys_and_interface():
+    net = build_net(INIT_CASES["mfgi_c2"], 0)
+    keys = list(net.state_dict().keys())
+    assert keys == ["decoder.fc_block.net.%d.0.%s" % (i, w) for i in range(6) for w in ("weight", "bias")]
+    assert net.decoder.fc_block.net[2][0].weight.shape == (256, 256)
+    with pytest.raises(ValueError):
+        digs_b200.DiGSNetwork(0, encoder_type="vae")
+    with pytest.raises(NotImplementedError):
+        digs_b200.DiGSNetwork(0, encoder_type="none", nl="relu")
+
+
+def test_cpu_tensors_fail_loudly():
+    net = build_net(INIT_CASES["geo"], 0)
+    pts = torch.zeros(1, 8, 3, requires_grad=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(pts, pts)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net.decoder(torch.zeros(8, 3))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "digs_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("no oracle", ""), fn
+            assert "/root/reference" not in src, fn
+
+
+@pytest.mark.parametrize("decay", ["linear", "quintic", "step", "none"])
+@pytest.mark.parametrize("pname,params", [("recipe", (1e2, 0.2, 1e2, 0.4, 0.0, 0.0)),
+                                          ("scene", (1e1, 0.1, 1e1, 0.3, 0.0, 0.0)), ("two", (50.0, 5.0))])
+def test_div_weight_schedule(decay, pname, params):
+    g = golden("div_weight.npz")
+    crit = digs_b200.DiGSLoss(weights=[3e3, 1e2, 1e2, 5e1, 1e2], loss_type="siren_wo_n_w_div", div_decay=decay,
+                              div_type="l1")
+    vals = []
+    for it in range(0, 1001, 25):
+        crit.update_div_weight(it, 1000, params)
+        vals.append(crit.weights[4])
+    np.testing.assert_allclose(np.array(vals), g["%s/%s" % (decay, pname)], rtol=0, atol=0)
+
+
+def test_loss_rejects_out_of_scope_modes():
+    crit = digs_b200.DiGSLoss(loss_type="siren_w_curv")
+    z = torch.zeros(1, 4, 3)
+    with pytest.raises(NotImplementedError):
+        crit({"nonmanifold_pnts_pred": z, "manifold_pnts_pred": z, "latent_reg": None, "latent": None}, z, z, z)
+    with pytest.raises(Warning):
+        digs_b200.DiGSLoss(loss_type="bogus")({"nonmanifold_pnts_pred": z, "manifold_pnts_pred": z,
+                                               "latent_reg": None, "latent": None}, z, z, z)
+
+
+@pytest.mark.parametrize("tag", ["cube16", "box20", "zshort12"])
+def test_grid_axes_match_reference(tag):
+    g = golden("grid.npz")
+    axes, length, short = grid_axes(int(g[tag + "/res"]), g[tag + "/bbox"])
+    for a, name in zip(axes, "xyz"):
+        np.testing.assert_array_equal(a, g["%s/%s" % (tag, name)])
+    # flat order [iy][ix][iz] of the reference's meshgrid(indexing='xy') ravel
+    pts = g[tag + "/points_f16"]
+    nx, ny, nz = (len(a) for a in axes)
+    assert pts.shape == (nx * ny * nz, 3)
+    iy, ix, iz = np.unravel_index(np.arange(pts.shape[0]), (ny, nx, nz))
+    np.testing.assert_array_equal(pts[:, 0], axes[0].astype(np.float16)[ix])
+    np.testing.assert_array_equal(pts[:, 1], axes[1].astype(np.float16)[iy])
+    np.testing.assert_array_equal(pts[:, 2], axes[2].astype(np.float16)[iz])
+
+
+def test_slab_and_shard_ranges_partition():
+    for n in (0, 1, 7, 512, 15000):
+        for world in (1, 2, 3, 8):
+            spans = [slab_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+            assert spans == [ddist.shard_range(n, r, world) for r in range(world)]
+
+
+def test_flat_grads_views():
+    lin = torch.nn.Linear(4, 3)
+    fg = ddist.FlatGrads(list(lin.parameters()), extra=8)
+    assert fg.flat.numel() == 12 + 3 + 8
+    lin.weight.grad.fill_(2.0)
+    assert float(fg.flat[:12].sum()) == 24.0
+    fg.zero_()
+    assert float(lin.weight.grad.abs().sum()) == 0.0
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from digs_b200 import dist as dd
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+torch.manual_seed(0)
+lin = torch.nn.Linear(6, 5)
+pts = torch.arange(2 * 11 * 3, dtype=torch.float32).reshape(2, 11, 3)
+mine = dd.shard_points(pts, rank, world)
+# a sum over point shards normalised by the GLOBAL count equals the single-process mean
+fg = dd.FlatGrads(list(lin.parameters()), extra=2)
+fg.flat[:3] = mine.sum(dim=(0, 1)) / (2 * 11)
+fg.extra[0] = float(mine.shape[1])
+fg.allreduce()
+ref = pts.mean(dim=(0, 1))
+assert torch.allclose(fg.flat[:3], ref, atol=1e-5), (fg.flat[:3], ref)
+assert int(fg.extra[0]) == 11
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_data_parallel_reduction_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29731")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out.decode()
