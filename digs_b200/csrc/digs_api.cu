@@ -1,4 +1,9 @@
 // C-ABI of libdigs_b200.so (see include/digs_b200.h): argument checking and dispatch on precision mode.
+//
+// DIGS_MODE_FP32   every kernel is the fp32 CUDA-core implementation (jet_simt.cu).
+// DIGS_MODE_BF16X2 / DIGS_MODE_BF16
+//                  forward jet, value query and grid query run on the tcgen05 kernel (jet_tc.cu); it leaves the same
+//                  `saved` layout behind as the fp32 path, and the reverse pass currently runs the fp32 kernels on it.
 #include "digs_internal.h"
 #include <cstdarg>
 #include <cstdio>
@@ -32,14 +37,35 @@ static int check_net(const DigsNet* net) {
         if (!net->W[l] || !net->b[l]) { set_error("net.W[%d]/b[%d] is NULL", l, l); return DIGS_EINVAL; }
     return DIGS_OK;
 }
-static int check_mode(int mode) {
+// mode must be known; tensor-core modes additionally need a supported width (never a silent fallback)
+static int check_mode(const DigsNet* net, int mode) {
     if (mode == DIGS_MODE_FP32) return DIGS_OK;
     if (mode == DIGS_MODE_BF16X2 || mode == DIGS_MODE_BF16) {
-        set_error("precision mode %d (tcgen05) is not built into this library yet", mode);
-        return DIGS_ENOTIMPL;
+        if (!tcpath::supported(net)) {
+            set_error("precision mode %d (tcgen05) needs H in {128,256,512}; got H=%d", mode, net->H);
+            return DIGS_ENOTIMPL;
+        }
+        return DIGS_OK;
     }
     set_error("unknown precision mode %d", mode);
     return DIGS_EINVAL;
+}
+static inline bool is_tc(int mode) { return mode != DIGS_MODE_FP32; }
+static inline int passes_of(int mode) { return mode == DIGS_MODE_BF16X2 ? 3 : 1; }
+static inline size_t max2(size_t a, size_t b) { return a > b ? a : b; }
+
+static PreSrc xyz_src(const DigsNet* net, const float* xyz, int64_t xyz_stride, const float* shape_bias, int64_t pps) {
+    PreSrc s{};
+    s.mode = 1;
+    s.din = net->d;
+    s.xyz = xyz;
+    s.xyz_stride = xyz_stride;
+    s.W0 = net->W[0];
+    s.w0_stride = net->w0_stride;
+    s.b0 = net->b[0];
+    s.shape_bias = shape_bias;
+    s.pps = pps > 0 ? pps : 1;
+    return s;
 }
 }  // namespace digs
 
@@ -52,23 +78,26 @@ const char* digs_last_error(void) { return g_err; }
 long long digs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 size_t digs_saved_bytes(const DigsNet* net, int64_t n, int want_lap, int mode) {
-    if (check_net(net) || check_mode(mode) || n < 0) return 0;
+    if (check_net(net) || check_mode(net, mode) || n < 0) return 0;
     return simt::saved_bytes(net, n, want_lap);
 }
 size_t digs_forward_workspace_bytes(const DigsNet* net, int64_t n, int want_lap, int mode) {
-    if (check_net(net) || check_mode(mode) || n < 0) return 0;
+    if (check_net(net) || check_mode(net, mode) || n < 0) return 0;
+    if (is_tc(mode)) return tcpath::prep_ws_bytes(net);
     return simt::fwd_ws_bytes(net, n, want_lap);
 }
 size_t digs_backward_workspace_bytes(const DigsNet* net, int64_t n, int want_lap, int mode) {
-    if (check_net(net) || check_mode(mode) || n < 0) return 0;
+    if (check_net(net) || check_mode(net, mode) || n < 0) return 0;
     return simt::bwd_ws_bytes(net, n, want_lap);
 }
 size_t digs_value_workspace_bytes(const DigsNet* net, int64_t n, int mode) {
-    if (check_net(net) || check_mode(mode) || n < 0) return 0;
+    if (check_net(net) || check_mode(net, mode) || n < 0) return 0;
+    if (is_tc(mode)) return tcpath::prep_ws_bytes(net);
     return simt::value_ws_bytes(net, n);
 }
 size_t digs_grid_workspace_bytes(const DigsNet* net, int mode) {
-    if (check_net(net) || check_mode(mode)) return 0;
+    if (check_net(net) || check_mode(net, mode)) return 0;
+    if (is_tc(mode)) return tcpath::prep_ws_bytes(net);
     return simt::grid_ws_bytes(net);
 }
 
@@ -76,7 +105,7 @@ int digs_jet_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t xy
                      int64_t pts_per_shape, int want_lap, float* f, float* grad, float* lap, void* saved,
                      size_t saved_bytes, void* workspace, size_t workspace_bytes, int mode, void* stream) {
     int rc;
-    if ((rc = check_net(net)) || (rc = check_mode(mode))) return rc;
+    if ((rc = check_net(net)) || (rc = check_mode(net, mode))) return rc;
     if (n < 0 || xyz_stride < net->d) { set_error("jet_forward: bad n/xyz_stride"); return DIGS_EINVAL; }
     if (n == 0) return DIGS_OK;
     if (!xyz || !f || !grad || (want_lap && !lap)) { set_error("jet_forward: NULL buffer"); return DIGS_EINVAL; }
@@ -85,10 +114,19 @@ int digs_jet_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t xy
         set_error("jet_forward: saved buffer too small (%zu < %zu)", saved_bytes, simt::saved_bytes(net, n, want_lap));
         return DIGS_ENOSPACE;
     }
-    size_t need = simt::fwd_ws_bytes(net, n, want_lap);
+    size_t need = digs_forward_workspace_bytes(net, n, want_lap, mode);
     if (!workspace || workspace_bytes < need) {
         set_error("jet_forward: workspace too small (%zu < %zu)", workspace_bytes, need);
         return DIGS_ENOSPACE;
+    }
+    if (is_tc(mode)) {
+        const int C = 1 + net->d + (want_lap ? 1 : 0);
+        float* planes = reinterpret_cast<float*>(saved);
+        float* headsv = saved ? reinterpret_cast<float*>(reinterpret_cast<char*>(saved) +
+                                                         align_up((size_t)net->Lh * C * n * net->H * sizeof(float), 256))
+                              : nullptr;
+        return tcpath::forward(net, xyz_src(net, xyz, xyz_stride, shape_bias, pts_per_shape), n, 1, want_lap, f, grad,
+                               lap, planes, headsv, workspace, passes_of(mode), (cudaStream_t)stream);
     }
     return simt::jet_forward(net, xyz, n, xyz_stride, shape_bias, pts_per_shape, want_lap, f, grad, lap, saved,
                              workspace, (cudaStream_t)stream);
@@ -100,7 +138,7 @@ int digs_jet_backward(const DigsNet* net, const float* xyz, int64_t n, int64_t x
                       size_t workspace_bytes, const DigsGrads* grads, float* shape_bias_grad, int mode,
                       void* stream) {
     int rc;
-    if ((rc = check_net(net)) || (rc = check_mode(mode))) return rc;
+    if ((rc = check_net(net)) || (rc = check_mode(net, mode))) return rc;
     if (n < 0 || xyz_stride < net->d) { set_error("jet_backward: bad n/xyz_stride"); return DIGS_EINVAL; }
     if (n == 0) return DIGS_OK;
     if (!xyz || !saved || !grads) { set_error("jet_backward: NULL buffer"); return DIGS_EINVAL; }
@@ -138,22 +176,16 @@ int digs_value_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t 
                        int64_t pts_per_shape, float* f, void* workspace, size_t workspace_bytes, int mode,
                        void* stream) {
     int rc;
-    if ((rc = check_net(net)) || (rc = check_mode(mode))) return rc;
+    if ((rc = check_net(net)) || (rc = check_mode(net, mode))) return rc;
     if (n < 0 || xyz_stride < net->d) { set_error("value_forward: bad n/xyz_stride"); return DIGS_EINVAL; }
     if (n == 0) return DIGS_OK;
     if (!xyz || !f) { set_error("value_forward: NULL buffer"); return DIGS_EINVAL; }
-    size_t need = simt::value_ws_bytes(net, n);
+    size_t need = digs_value_workspace_bytes(net, n, mode);
     if (!workspace || workspace_bytes < need) { set_error("value_forward: workspace too small"); return DIGS_ENOSPACE; }
-    PreSrc s{};
-    s.mode = 1;
-    s.din = net->d;
-    s.xyz = xyz;
-    s.xyz_stride = xyz_stride;
-    s.W0 = net->W[0];
-    s.w0_stride = net->w0_stride;
-    s.b0 = net->b[0];
-    s.shape_bias = shape_bias;
-    s.pps = pts_per_shape > 0 ? pts_per_shape : 1;
+    PreSrc s = xyz_src(net, xyz, xyz_stride, shape_bias, pts_per_shape);
+    if (is_tc(mode))
+        return tcpath::forward(net, s, n, 0, 0, f, nullptr, nullptr, nullptr, nullptr, workspace, passes_of(mode),
+                               (cudaStream_t)stream);
     return simt::value_forward(net, s, n, f, workspace, (cudaStream_t)stream);
 }
 
@@ -161,7 +193,7 @@ int digs_grid_query(const DigsNet* net, const uint16_t* x_fp16, int nx, const ui
                     const uint16_t* z_fp16, int nz, int iy_begin, int iy_end, const float* shape_bias, float* sdf_out,
                     void* workspace, size_t workspace_bytes, int mode, void* stream) {
     int rc;
-    if ((rc = check_net(net)) || (rc = check_mode(mode))) return rc;
+    if ((rc = check_net(net)) || (rc = check_mode(net, mode))) return rc;
     if (net->d != 3) { set_error("grid_query: d must be 3"); return DIGS_EINVAL; }
     if (nx <= 0 || ny <= 0 || nz <= 0 || iy_begin < 0 || iy_end > ny || iy_begin > iy_end) {
         set_error("grid_query: bad grid extents");
@@ -169,8 +201,24 @@ int digs_grid_query(const DigsNet* net, const uint16_t* x_fp16, int nx, const ui
     }
     if (iy_begin == iy_end) return DIGS_OK;
     if (!x_fp16 || !y_fp16 || !z_fp16 || !sdf_out) { set_error("grid_query: NULL buffer"); return DIGS_EINVAL; }
-    size_t need = simt::grid_ws_bytes(net);
+    size_t need = digs_grid_workspace_bytes(net, mode);
     if (!workspace || workspace_bytes < need) { set_error("grid_query: workspace too small"); return DIGS_ENOSPACE; }
+    if (is_tc(mode)) {
+        PreSrc s{};
+        s.mode = 2;
+        s.din = 3;
+        s.shape_bias = shape_bias;
+        s.pps = (int64_t)1 << 62;
+        s.ax = reinterpret_cast<const __half*>(x_fp16);
+        s.ay = reinterpret_cast<const __half*>(y_fp16);
+        s.az = reinterpret_cast<const __half*>(z_fp16);
+        s.nx = nx;
+        s.nz = nz;
+        s.grid_base = (int64_t)iy_begin * nx * nz;
+        int64_t total = (int64_t)(iy_end - iy_begin) * nx * nz;
+        return tcpath::forward(net, s, total, 0, 0, sdf_out, nullptr, nullptr, nullptr, nullptr, workspace,
+                               passes_of(mode), (cudaStream_t)stream);
+    }
     return simt::grid_query(net, x_fp16, nx, y_fp16, ny, z_fp16, nz, iy_begin, iy_end, shape_bias, sdf_out, workspace,
                             (cudaStream_t)stream);
 }

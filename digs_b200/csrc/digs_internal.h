@@ -54,6 +54,15 @@ int grid_query(const DigsNet* net, const uint16_t* xh, int nx, const uint16_t* y
                int nz, int iy_begin, int iy_end, const float* shape_bias, float* out, void* ws, cudaStream_t st);
 }  // namespace simt
 
+// ---- tcgen05 path (jet_tc.cu) ------------------------------------------------------------------
+namespace tcpath {
+bool supported(const DigsNet* net);
+size_t prep_ws_bytes(const DigsNet* net);
+// want_jet = 0: value channel only.  planes/head_saved: NULL or the SIMT `saved` layout.  passes: 3 (bf16x2) or 1 (bf16).
+int forward(const DigsNet* net, const PreSrc& src, int64_t n, int want_jet, int want_lap, float* f, float* grad,
+            float* lap, float* planes, float* head_saved, void* ws, int passes, cudaStream_t st);
+}  // namespace tcpath
+
 // ---- fused loss (loss_fused.cu) -------------------------------------------------------------
 int loss_fused(const float* f_m, const float* g_m, int64_t nm, const float* f_n, const float* g_n,
                const float* lap_n, int64_t nn, const float* normals, int d, const float* weights,
