@@ -2,8 +2,8 @@
 //
 // DIGS_MODE_FP32   every kernel is the fp32 CUDA-core implementation (jet_simt.cu).
 // DIGS_MODE_BF16X2 / DIGS_MODE_BF16
-//                  forward jet, value query and grid query run on the tcgen05 kernel (jet_tc.cu); it leaves the same
-//                  `saved` layout behind as the fp32 path, and the reverse pass currently runs the fp32 kernels on it.
+//                  forward jet, value / grid query, reverse pass and weight gradients run on the tcgen05 kernels
+//                  (jet_tc.cu, wgrad_tc.cu); only the per-point head adjoint reuses a small fp32 kernel.
 #include "digs_internal.h"
 #include <cstdarg>
 #include <cstdio>
@@ -79,6 +79,7 @@ long long digs_launch_count(void) { return g_launches.load(std::memory_order_rel
 
 size_t digs_saved_bytes(const DigsNet* net, int64_t n, int want_lap, int mode) {
     if (check_net(net) || check_mode(net, mode) || n < 0) return 0;
+    if (is_tc(mode)) return tcpath::saved_bytes(net, n, want_lap);
     return simt::saved_bytes(net, n, want_lap);
 }
 size_t digs_forward_workspace_bytes(const DigsNet* net, int64_t n, int want_lap, int mode) {
@@ -88,6 +89,7 @@ size_t digs_forward_workspace_bytes(const DigsNet* net, int64_t n, int want_lap,
 }
 size_t digs_backward_workspace_bytes(const DigsNet* net, int64_t n, int want_lap, int mode) {
     if (check_net(net) || check_mode(net, mode) || n < 0) return 0;
+    if (is_tc(mode)) return tcpath::bwd_ws_bytes(net, n, want_lap);
     return simt::bwd_ws_bytes(net, n, want_lap);
 }
 size_t digs_value_workspace_bytes(const DigsNet* net, int64_t n, int mode) {
@@ -110,8 +112,8 @@ int digs_jet_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t xy
     if (n == 0) return DIGS_OK;
     if (!xyz || !f || !grad || (want_lap && !lap)) { set_error("jet_forward: NULL buffer"); return DIGS_EINVAL; }
     if (shape_bias && pts_per_shape <= 0) { set_error("jet_forward: pts_per_shape <= 0"); return DIGS_EINVAL; }
-    if (saved && saved_bytes < simt::saved_bytes(net, n, want_lap)) {
-        set_error("jet_forward: saved buffer too small (%zu < %zu)", saved_bytes, simt::saved_bytes(net, n, want_lap));
+    if (saved && saved_bytes < digs_saved_bytes(net, n, want_lap, mode)) {
+        set_error("jet_forward: saved buffer too small (%zu < %zu)", saved_bytes, digs_saved_bytes(net, n, want_lap, mode));
         return DIGS_ENOSPACE;
     }
     size_t need = digs_forward_workspace_bytes(net, n, want_lap, mode);
@@ -119,15 +121,9 @@ int digs_jet_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t xy
         set_error("jet_forward: workspace too small (%zu < %zu)", workspace_bytes, need);
         return DIGS_ENOSPACE;
     }
-    if (is_tc(mode)) {
-        const int C = 1 + net->d + (want_lap ? 1 : 0);
-        float* planes = reinterpret_cast<float*>(saved);
-        float* headsv = saved ? reinterpret_cast<float*>(reinterpret_cast<char*>(saved) +
-                                                         align_up((size_t)net->Lh * C * n * net->H * sizeof(float), 256))
-                              : nullptr;
+    if (is_tc(mode))
         return tcpath::forward(net, xyz_src(net, xyz, xyz_stride, shape_bias, pts_per_shape), n, 1, want_lap, f, grad,
-                               lap, planes, headsv, workspace, passes_of(mode), (cudaStream_t)stream);
-    }
+                               lap, saved, workspace, passes_of(mode), (cudaStream_t)stream);
     return simt::jet_forward(net, xyz, n, xyz_stride, shape_bias, pts_per_shape, want_lap, f, grad, lap, saved,
                              workspace, (cudaStream_t)stream);
 }
@@ -148,12 +144,16 @@ int digs_jet_backward(const DigsNet* net, const float* xyz, int64_t n, int64_t x
         set_error("jet_backward: shape_bias given without shape_bias_grad/pts_per_shape");
         return DIGS_EINVAL;
     }
-    if (saved_bytes < simt::saved_bytes(net, n, want_lap)) { set_error("jet_backward: saved buffer too small"); return DIGS_ENOSPACE; }
-    size_t need = simt::bwd_ws_bytes(net, n, want_lap);
+    if (saved_bytes < digs_saved_bytes(net, n, want_lap, mode)) { set_error("jet_backward: saved buffer too small"); return DIGS_ENOSPACE; }
+    size_t need = digs_backward_workspace_bytes(net, n, want_lap, mode);
     if (!workspace || workspace_bytes < need) {
         set_error("jet_backward: workspace too small (%zu < %zu)", workspace_bytes, need);
         return DIGS_ENOSPACE;
     }
+    if (is_tc(mode))
+        return tcpath::backward(net, xyz_src(net, xyz, xyz_stride, shape_bias, pts_per_shape), n, want_lap, f_bar,
+                                grad_bar, lap_bar, saved, workspace, grads, shape_bias ? shape_bias_grad : nullptr,
+                                passes_of(mode), (cudaStream_t)stream);
     return simt::jet_backward(net, xyz, n, xyz_stride, shape_bias, pts_per_shape, want_lap, f_bar, grad_bar, lap_bar,
                               saved, workspace, grads, shape_bias ? shape_bias_grad : nullptr, (cudaStream_t)stream);
 }
@@ -184,7 +184,7 @@ int digs_value_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t 
     if (!workspace || workspace_bytes < need) { set_error("value_forward: workspace too small"); return DIGS_ENOSPACE; }
     PreSrc s = xyz_src(net, xyz, xyz_stride, shape_bias, pts_per_shape);
     if (is_tc(mode))
-        return tcpath::forward(net, s, n, 0, 0, f, nullptr, nullptr, nullptr, nullptr, workspace, passes_of(mode),
+        return tcpath::forward(net, s, n, 0, 0, f, nullptr, nullptr, nullptr, workspace, passes_of(mode),
                                (cudaStream_t)stream);
     return simt::value_forward(net, s, n, f, workspace, (cudaStream_t)stream);
 }
@@ -216,8 +216,8 @@ int digs_grid_query(const DigsNet* net, const uint16_t* x_fp16, int nx, const ui
         s.nz = nz;
         s.grid_base = (int64_t)iy_begin * nx * nz;
         int64_t total = (int64_t)(iy_end - iy_begin) * nx * nz;
-        return tcpath::forward(net, s, total, 0, 0, sdf_out, nullptr, nullptr, nullptr, nullptr, workspace,
-                               passes_of(mode), (cudaStream_t)stream);
+        return tcpath::forward(net, s, total, 0, 0, sdf_out, nullptr, nullptr, nullptr, workspace, passes_of(mode),
+                               (cudaStream_t)stream);
     }
     return simt::grid_query(net, x_fp16, nx, y_fp16, ny, z_fp16, nz, iy_begin, iy_end, shape_bias, sdf_out, workspace,
                             (cudaStream_t)stream);

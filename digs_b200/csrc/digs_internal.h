@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
 #include <stdint.h>
 #include <stddef.h>
 #include "../../include/digs_b200.h"
@@ -52,15 +54,36 @@ int jet_backward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_st
 int value_forward(const DigsNet* net, const PreSrc& src0, int64_t n, float* f, void* ws, cudaStream_t st);
 int grid_query(const DigsNet* net, const uint16_t* xh, int nx, const uint16_t* yh, int ny, const uint16_t* zh,
                int nz, int iy_begin, int iy_end, const float* shape_bias, float* out, void* ws, cudaStream_t st);
+// head adjoint per point: (f_bar, g_bar, l_bar) + head_saved -> ubar [n][C]; db_last += sum u_bar
+int head_seed(const DigsNet* net, int64_t n, int want_lap, const float* head_saved, const float* f_bar,
+              const float* g_bar, const float* l_bar, float* ubar, float* db_last, cudaStream_t st);
 }  // namespace simt
 
-// ---- tcgen05 path (jet_tc.cu) ------------------------------------------------------------------
+// ---- tcgen05 path (jet_tc.cu, wgrad_tc.cu) ----------------------------------------------------
 namespace tcpath {
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode();   // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda dependency)
+int num_sms();
+struct SavedLayout {     // what the tensor-core forward leaves for the reverse pass
+    int C;
+    int64_t n_pad;
+    size_t planes_bytes, act_bytes, head_bytes;
+};
+SavedLayout saved_layout(const DigsNet* net, int64_t n, int want_lap);
 bool supported(const DigsNet* net);
 size_t prep_ws_bytes(const DigsNet* net);
-// want_jet = 0: value channel only.  planes/head_saved: NULL or the SIMT `saved` layout.  passes: 3 (bf16x2) or 1 (bf16).
+size_t saved_bytes(const DigsNet* net, int64_t n, int want_lap);
+size_t bwd_ws_bytes(const DigsNet* net, int64_t n, int want_lap);
+// want_jet = 0: value channel only.  saved: NULL or saved_bytes() bytes.  passes: 3 (bf16x2) or 1 (bf16).
 int forward(const DigsNet* net, const PreSrc& src, int64_t n, int want_jet, int want_lap, float* f, float* grad,
-            float* lap, float* planes, float* head_saved, void* ws, int passes, cudaStream_t st);
+            float* lap, void* saved, void* ws, int passes, cudaStream_t st);
+int backward(const DigsNet* net, const PreSrc& src, int64_t n, int want_lap, const float* f_bar, const float* g_bar,
+             const float* l_bar, const void* saved, void* ws, const DigsGrads* grads, float* sb_grad, int passes,
+             cudaStream_t st);
+int wgrad(const DigsNet* net, const __nv_bfloat16* GT, const __nv_bfloat16* actT, int C, int64_t n_pad,
+          const DigsGrads* grads, int passes, cudaStream_t st);
 }  // namespace tcpath
 
 // ---- fused loss (loss_fused.cu) -------------------------------------------------------------

@@ -810,5 +810,22 @@ int jet_backward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_st
     return backward_t<2, 0>(net, src0, n, f_bar, g_bar, l_bar, planes, headsv, w, grads, shape_bias_grad, st);
 }
 
+int head_seed(const DigsNet* net, int64_t n, int want_lap, const float* head_saved, const float* f_bar,
+              const float* g_bar, const float* l_bar, float* ubar, float* db_last, cudaStream_t st) {
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (net->d == 3 && want_lap)
+        k_head_seed<3, 1><<<blocks, 256, 0, st>>>(head_saved, f_bar, g_bar, l_bar, net->head, net->scale, ubar, db_last, n);
+    else if (net->d == 3)
+        k_head_seed<3, 0><<<blocks, 256, 0, st>>>(head_saved, f_bar, g_bar, l_bar, net->head, net->scale, ubar, db_last, n);
+    else if (want_lap)
+        k_head_seed<2, 1><<<blocks, 256, 0, st>>>(head_saved, f_bar, g_bar, l_bar, net->head, net->scale, ubar, db_last, n);
+    else
+        k_head_seed<2, 0><<<blocks, 256, 0, st>>>(head_saved, f_bar, g_bar, l_bar, net->head, net->scale, ubar, db_last, n);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("head_seed launch: %s", cudaGetErrorString(e)); return DIGS_ECUDA; }
+    return DIGS_OK;
+}
+
 }  // namespace simt
 }  // namespace digs

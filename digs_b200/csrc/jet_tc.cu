@@ -1,27 +1,33 @@
-// tcgen05 / TMEM / TMA implementation of the forward jet and the grid query (DIGS_MODE_BF16X2, DIGS_MODE_BF16).
+// tcgen05 / TMEM / TMA implementation of the jet path (DIGS_MODE_BF16X2, DIGS_MODE_BF16): forward jet, grid / value
+// query, and the reverse pass through the network (dgrad); the weight-gradient GEMM lives in wgrad_tc.cu.
 //
 // Reference behaviour reproduced: FCBlock.forward (models/DiGS.py:122-134) for a whole network per point tile,
-// plus the gradient / Laplacian channels the reference obtains from utils.gradient (utils/utils.py:108-117,
-// models/losses.py:72-76,100-106), and the chunk loop of utils.implicit2mesh (utils/utils.py:343-348).
+// the gradient / Laplacian channels the reference obtains from utils.gradient (utils/utils.py:108-117,
+// models/losses.py:72-76,100-106), the chunk loop of utils.implicit2mesh (utils/utils.py:343-348), and the
+// network part of loss.backward() (train_surface_reconstruction.py:128).
 //
 // One persistent CTA per SM walks point tiles.  A tile is T points x C jet channels = N <= 128 operand columns
-// (column = channel*T + point).  For every hidden layer the CTA computes, on the tensor cores,
+// (column = channel*T + point).  Every hidden layer is evaluated TRANSPOSED on the tensor cores:
 //
-//        D[unit][column] = sum_k (30 W)[unit][k] * X[column][k]          M = H units (H/128 UMMA tiles), N columns, K = H
+//   forward   D[unit][col]   = sum_k (30 W_l)[unit][k]  * X[col][k]        A = 30 W_l      (K-major,  TMA ring)
+//   reverse   D[k][col]      = sum_u (30 W_l)[u][k]     * Zhat[col][u]     A = (30 W_l)^T  (K-major,  TMA ring)
 //
-// i.e. the layer is evaluated TRANSPOSED: units sit on TMEM lanes, jet channels of a point sit in TMEM columns of
-// the same lane, so the sin/cos + jet recurrences of one (unit, point) need only the registers of one thread.
-//   A = 30*W   bf16 (hi [+ lo]) K-major SWIZZLE_128B tiles of 128 units x 64 k, streamed from L2 by TMA through a
-//              5-stage mbarrier ring (weights never live in shared memory as a whole);
-//   B = X      bf16 (hi [+ lo]) MN-major SWIZZLE_128B, written in place by the epilogue warps as the NEXT layer's
-//              operand: a thread owns one unit = one k row and stores 8 consecutive points as one 16-byte chunk;
-//   D          fp32 in TMEM, H/128 tiles of N columns; read back with tcgen05.ld.32x32b.
-// DIGS_MODE_BF16X2 runs three MMA passes per product (hi*hi + hi*lo + lo*hi, fp32 accumulate) which keeps ~16
-// mantissa bits per operand; DIGS_MODE_BF16 runs the hi*hi pass only.  Layer 0 (K = d) and the last layer (N = 1)
-// are fp32 FMAs / warp reductions from registers and never touch the tensor cores.
+// so units sit on TMEM lanes and the C jet channels of a point sit in TMEM columns of the same lane: the sin/cos
+// + jet recurrences (forward) and their adjoints (reverse) of one (unit, point) need only one thread's registers.
+//   A   bf16 hi [+ lo] tiles of 128 rows x 64 k, SWIZZLE_128B, streamed from L2 by TMA through a 5-stage mbarrier ring;
+//   B   bf16 hi [+ lo], MN-major SWIZZLE_128B, written IN PLACE by the epilogue warps as the next layer's operand:
+//       a thread owns one unit = one k row of B and stores 4 consecutive points as one 8-byte piece;
+//   D   fp32 in TMEM (H/128 tiles of N columns), read back with tcgen05.ld.32x32b.x4.
+// DIGS_MODE_BF16X2 runs three MMA passes per product (hi*hi + hi*lo + lo*hi); DIGS_MODE_BF16 runs hi*hi only.
+// Layer 0 (K = d) and the last layer (N = 1) are fp32 FMAs / warp reductions from registers.
 //
-// Warp roles (320 threads): warps 0-7 epilogue (TMEM -> registers -> jet math -> next operand / outputs),
-// warp 8 TMA producer, warp 9 MMA issuer + TMEM owner.
+// What the forward leaves in `saved` for the reverse pass (per cloud, n_pad = n rounded up to 8):
+//   planes_t [Lh][C][H][n_pad] fp32   pre-activations scaled by 30: (30 z | 30 Z_k | 30 Q), point-contiguous
+//   actT     [Lh][2][H][C*n_pad] bf16 layer inputs (h | A_k | P) of layers 1..Lh as hi/lo rows = wgrad operand
+//   head     [n][C] fp32              (u | gu_k | lu)
+// and the reverse kernel writes GT [Lh][2][H][C*n_pad] bf16 = adjoints (zbar | Zbar_k | Qbar)/30, the other wgrad operand.
+//
+// Warp roles (576 threads): warps 0-15 epilogue, warp 16 TMA producer, warp 17 MMA issuer + TMEM owner.
 #include "digs_internal.h"
 #include "tc_common.cuh"
 #include <cuda.h>
@@ -31,17 +37,19 @@ namespace tcpath {
 
 using namespace digs::tc;
 
-constexpr int NTHREADS = 320;
-constexpr int EPI_THREADS = 256;
+constexpr int EPI_WARPS = 16;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int NTHREADS = EPI_THREADS + 64;
 constexpr int STAGES = 5;
-constexpr int STAGE_BYTES = 128 * 64 * 2;  // one A tile: 128 units x 64 k, bf16
+constexpr int STAGE_BYTES = 128 * 64 * 2;  // one A tile: 128 rows x 64 k, bf16
 
 template <int D, int LAP, int H_, int PASSES>
 struct Cfg {
     static constexpr int C = 1 + D + LAP;
     static constexpr int H = H_;
-    static constexpr int N = (H_ > 256) ? 64 : 128;  // UMMA N (operand columns); 64 keeps X within shared memory at H=512
-    static constexpr int T = (N / C) / 8 * 8;         // points per tile (multiple of 8: one 16 B chunk of a k row)
+    static constexpr int N = (H_ > 256) ? 64 : 128;   // UMMA N (operand columns); 64 keeps X in shared memory at H=512
+    static constexpr int T = (N / C) / 8 * 8;         // points per tile
+    static constexpr int NGRP = T / 4;                // 4-point groups
     static constexpr int MT = H / 128;                // UMMA M tiles
     static constexpr int NG = N / 64;                 // 64-column groups of the MN-major operand
     static constexpr int SN = 1024;                   // byte stride between column groups   (descriptor LBO)
@@ -50,21 +58,22 @@ struct Cfg {
     static constexpr int NPARTS = (PASSES == 3) ? 2 : 1;
     static constexpr int KSLABS = H / 64;
     static constexpr int TMEM_COLS = (MT * N <= 128) ? 128 : ((MT * N <= 256) ? 256 : 512);
-    static constexpr int UPW = (MT >= 2) ? MT / 2 : 1;   // 32-unit blocks per epilogue warp
-    static constexpr int GSPLIT = (MT == 1) ? 2 : 1;     // point groups split between the two warp halves
-    static constexpr int NSLOT = (MT == 1) ? 4 : 8;      // head partial-sum slots
+    static constexpr int NUB = H / 32;                // 32-unit blocks
+    static constexpr int GS = EPI_WARPS / NUB;        // epilogue warps sharing one unit block (split over point groups)
     static constexpr int OFF_RING = B_PART * NPARTS;
     static constexpr int OFF_XYZ = OFF_RING + STAGES * STAGE_BYTES;
     static constexpr int OFF_HEAD = OFF_XYZ + 128 * 3 * 4;
-    static constexpr int OFF_BAR = OFF_HEAD + NSLOT * N * 4;
+    static constexpr int OFF_UBAR = OFF_HEAD + NUB * N * 4;
+    static constexpr int OFF_BAR = OFF_UBAR + N * 4;
     static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
-    static_assert(H % 128 == 0 && H <= 512, "H must be 128, 256, 384 or 512");
+    static_assert(H == 128 || H == 256 || H == 512, "H must be 128, 256 or 512");
     static_assert(MT * N <= 512, "accumulators exceed TMEM");
+    static_assert(EPI_WARPS % NUB == 0, "unit blocks must divide the epilogue warps");
 };
 
 struct Args {
-    PreSrc src;               // layer-0 input (xyz or grid), W0/b0 fields unused here
-    int64_t n;                // points
+    PreSrc src;               // layer-0 input (points or grid indices)
+    int64_t n, n_pad;
     int Lh;
     const float* w0_30;       // [H][4]: 30*W0[u][0..2], 30*b0[u]
     const float* bias30;      // [Lh][H]: 30*b_l[u], l = 1..Lh
@@ -72,11 +81,19 @@ struct Args {
     const float* b_last;      // [1]
     int head;
     float radius, scale;
-    float* f;                 // (n)
-    float* grad;              // (n, D)
-    float* lap;               // (n)
-    float* planes;            // NULL or [Lh][C][n][H] pre-activations (z, Z_k, Q) for the reverse pass
-    float* head_saved;        // NULL or [n][C]
+    float* f;                 // forward outputs
+    float* grad;
+    float* lap;
+    float* planes_t;          // forward: written (or NULL); reverse: read
+    __nv_bfloat16* actT;      // forward: written (or NULL)
+    float* head_saved;        // forward: written (or NULL)
+    const float* ubar;        // reverse: [n][C] head adjoints (u_bar | gu_bar_k | lu_bar)
+    __nv_bfloat16* GT;        // reverse: written
+    float* db[DIGS_MAX_LAYERS];  // reverse: bias gradients, layers 0..Lh (accumulated)
+    float* dW0;               // reverse: (H, w0_stride), first d columns accumulated
+    int w0_stride;
+    float* dw_last;           // reverse: (H)
+    float* sb_grad;           // reverse: (n_shapes, H) or NULL
 };
 
 // sin/cos of a phase of any magnitude: two-constant Cody-Waite reduction to [-pi, pi], then MUFU
@@ -89,78 +106,60 @@ __device__ __forceinline__ void sincos_reduced(float t, float& s, float& c) {
     c = __cosf(r);
 }
 
-// value t = 30 z, Zp = 30 Z_k, Qp = 30 Q  ->  next-layer inputs (h, A_k, P)
-template <int D, int LAP>
-__device__ __forceinline__ void act_scaled(float t, const float* Zp, float Qp, float* o) {
-    float s, c;
-    sincos_reduced(t, s, c);
-    o[0] = s;
-    if constexpr (D > 0) {
-        float S2 = 0.f;
+// Sum NV (<= 32) per-lane values over the 32 lanes.  x[] is padded to P = 4, 16 or 32 entries; afterwards x[0] of
+// lane j (j < P) holds the total of value j.
+template <int P>
+__device__ __forceinline__ void warp_reduce_scatter(float* x, int lane) {
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            o[1 + j] = c * Zp[j];
-            S2 = fmaf(Zp[j], Zp[j], S2);
-        }
-        if constexpr (LAP) o[1 + D] = fmaf(c, Qp, -s * S2);
-    }
-}
-
-// sum over the 32 lanes of NV (multiple of 8) per-lane values; afterwards lane j holds total of value j for the
-// first 32-blocks, and lane (j % 8) of every 8-lane group holds value j of a trailing 8-block.
-template <int NV>
-__device__ __forceinline__ void warp_reduce_scatter(float* v, int lane) {
-    constexpr int FULL = NV / 32;
+    for (int off = 16; off >= P; off >>= 1)
 #pragma unroll
-    for (int b = 0; b < FULL; ++b) {
-        float* x = v + 32 * b;
+        for (int j = 0; j < P; ++j) x[j] += __shfl_xor_sync(0xffffffffu, x[j], off);
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const bool up = (lane & off) != 0;
+    for (int off = P / 2; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
 #pragma unroll
-            for (int j = 0; j < off; ++j) {
-                float send = up ? x[j] : x[j + off];
-                float keep = up ? x[j + off] : x[j];
-                x[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
-        }
-    }
-    constexpr int REM = (NV % 32) / 8;
-#pragma unroll
-    for (int b = 0; b < REM; ++b) {
-        float* x = v + 32 * FULL + 8 * b;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            x[j] += __shfl_xor_sync(0xffffffffu, x[j], 16);
-            x[j] += __shfl_xor_sync(0xffffffffu, x[j], 8);
-        }
-#pragma unroll
-        for (int off = 4; off >= 1; off >>= 1) {
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int j = 0; j < off; ++j) {
-                float send = up ? x[j] : x[j + off];
-                float keep = up ? x[j + off] : x[j];
-                x[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
+        for (int j = 0; j < off; ++j) {
+            float send = up ? x[j] : x[j + off];
+            float keep = up ? x[j + off] : x[j];
+            x[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
         }
     }
 }
 
-template <int D, int LAP, int H, int PASSES>
-__global__ void __launch_bounds__(NTHREADS, 1) k_tc_forward(const __grid_constant__ CUtensorMap tmapW, Args a) {
+__device__ __forceinline__ void point_coords(const PreSrc& s, int64_t gp, float& x, float& y, float& z) {
+    if (s.mode == 2) {
+        int64_t g = s.grid_base + gp;
+        int iz = (int)(g % s.nz);
+        int64_t t2 = g / s.nz;
+        int ix = (int)(t2 % s.nx);
+        int iy = (int)(t2 / s.nx);
+        x = __half2float(s.ax[ix]);
+        y = __half2float(s.ay[iy]);
+        z = __half2float(s.az[iz]);
+    } else {
+        const float* xp = s.xyz + gp * s.xyz_stride;
+        x = __ldg(xp);
+        y = __ldg(xp + 1);
+        z = (s.din > 2) ? __ldg(xp + 2) : 0.f;
+    }
+}
+
+template <int D, int LAP, int H, int PASSES, bool BWD>
+__global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ CUtensorMap tmapW, Args a) {
     using G = Cfg<D, LAP, H, PASSES>;
     constexpr int C = G::C, T = G::T, N = G::N, MT = G::MT;
+    constexpr int P2 = (C * 4 <= 4) ? 4 : ((C * 4 <= 16) ? 16 : 32);   // padded size of the head partial-sum vector
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sB = smem;
     uint8_t* sRing = smem + G::OFF_RING;
     float* sXyz = reinterpret_cast<float*>(smem + G::OFF_XYZ);
     float* sHead = reinterpret_cast<float*>(smem + G::OFF_HEAD);
+    float* sUbar = reinterpret_cast<float*>(smem + G::OFF_UBAR);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
-    uint64_t* w_full = bars;                 // [STAGES]
-    uint64_t* w_empty = bars + STAGES;       // [STAGES]
-    uint64_t* b_ready = bars + 2 * STAGES;   // epilogue -> MMA: next operand complete (256 arrivals)
+    uint64_t* w_full = bars;                      // [STAGES]
+    uint64_t* w_empty = bars + STAGES;            // [STAGES]
+    uint64_t* b_ready = bars + 2 * STAGES;        // epilogue -> MMA: next operand complete (512 arrivals)
     uint64_t* acc_ready = bars + 2 * STAGES + 1;  // MMA -> epilogue: accumulators complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
 
@@ -172,7 +171,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_forward(const __grid_constan
         fence_barrier_init();
         tma_prefetch_desc(&tmapW);
     }
-    if (warp == 9) tmem_alloc<G::TMEM_COLS>(tmem_slot);
+    if (warp == EPI_WARPS + 1) tmem_alloc<G::TMEM_COLS>(tmem_slot);
     for (int i = tid; i < G::OFF_RING / 16; i += NTHREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
@@ -182,41 +181,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_forward(const __grid_constan
     const int64_t num_tiles = (a.n + T - 1) / T;
     const int Lh = a.Lh;
 
-    if (warp == 8) {
-        // ================= TMA producer: stream 30*W tiles (hi, lo) in the order the MMA warp consumes them ========
+    if (warp == EPI_WARPS) {
+        // ================= TMA producer: stream weight tiles (hi, lo) in the order the MMA warp consumes them =====
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                for (int l = 1; l <= Lh; ++l)
+            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+                for (int j = 0; j < Lh; ++j) {
+                    const int l = BWD ? (Lh - j) : (j + 1);
                     for (int ks = 0; ks < G::KSLABS; ++ks)
                         for (int m = 0; m < MT; ++m)
                             for (int part = 0; part < G::NPARTS; ++part) {
                                 mbar_wait(&w_empty[stage], phase ^ 1);
                                 mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
+                                // rows: [dir = fwd|transposed][part = hi|lo][layer][H]
                                 tma_load_2d(sRing + stage * STAGE_BYTES, &tmapW, &w_full[stage], ks * 64,
-                                            (part * Lh + (l - 1)) * H + m * 128);
+                                            (((BWD ? 2 : 0) + part) * Lh + (l - 1)) * H + m * 128);
                                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
                             }
-            }
+                }
         }
-    } else if (warp == 9) {
+    } else if (warp == EPI_WARPS + 1) {
         // ================= MMA issuer ============================================================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, N, /*A K-major*/ 0, /*B MN-major*/ 1);
             const uint32_t sB_hi = smem_u32(sB), sB_lo = smem_u32(sB) + G::B_PART;
             int stage = 0;
             uint32_t phase = 0, pb = 0;
-            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                for (int l = 1; l <= Lh; ++l) {
+            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+                for (int j = 0; j < Lh; ++j) {
                     mbar_wait(b_ready, pb);
                     pb ^= 1;
                     tc_fence_after();
                     for (int ks = 0; ks < G::KSLABS; ++ks)
                         for (int m = 0; m < MT; ++m) {
                             const uint32_t d_tmem = tmem_base + m * N;
-                            // --- A_hi tile: hi*hi (+ hi*lo)
-                            mbar_wait(&w_full[stage], phase);
+                            mbar_wait(&w_full[stage], phase);   // A_hi tile: hi*hi (+ hi*lo)
                             tc_fence_after();
                             {
                                 const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
@@ -235,8 +235,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_forward(const __grid_constan
                             umma_commit(&w_empty[stage]);
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                             if constexpr (PASSES == 3) {
-                                // --- A_lo tile: lo*hi
-                                mbar_wait(&w_full[stage], phase);
+                                mbar_wait(&w_full[stage], phase);   // A_lo tile: lo*hi
                                 tc_fence_after();
                                 const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
 #pragma unroll
@@ -252,161 +251,233 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_forward(const __grid_constan
                         }
                     umma_commit(acc_ready);
                 }
-            }
         }
     } else {
-        // ================= epilogue warps 0..7 ===================================================================
-        const int q = warp & 3;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const int slot = (MT == 1) ? q : warp;
-        const int g0 = (MT == 1) ? (warp >> 2) : 0;
+        // ================= epilogue warps 0..15 ==================================================================
+        const int ub = warp % G::NUB;          // 32-unit block; ub % 4 == warp % 4 = TMEM lane quarter of this warp
+        const int gpart = warp / G::NUB;       // which share of the point groups
+        const int u = ub * 32 + lane;          // unit index
+        const int mt = ub >> 2;
+        const uint32_t lane_base = (uint32_t)((ub & 3) * 32) << 16;
         uint32_t pa = 0;
-        // per-unit constants
-        int units[G::UPW];
-        float w0x[G::UPW], w0y[G::UPW], w0z[G::UPW], b0[G::UPW], wl[G::UPW];
-#pragma unroll
-        for (int ui = 0; ui < G::UPW; ++ui) {
-            int mt = (MT >= 2) ? ((warp >> 2) + 2 * ui) : 0;
-            int u = mt * 128 + q * 32 + lane;
-            units[ui] = u;
-            float4 w = __ldg(reinterpret_cast<const float4*>(a.w0_30) + u);
-            w0x[ui] = w.x; w0y[ui] = w.y; w0z[ui] = w.z; b0[ui] = w.w;
-            wl[ui] = __ldg(a.w_last + u);
-        }
-        const int64_t ps = a.n * (int64_t)H;
+        const float4 w0v = __ldg(reinterpret_cast<const float4*>(a.w0_30) + u);
+        const float wl = __ldg(a.w_last + u);
+        const int64_t rowlen = (int64_t)C * a.n_pad;     // row length of actT / GT
+        const uint32_t rowoff = (uint32_t)(u >> 3) * G::SK + (uint32_t)(u & 7) * 128;
 
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int64_t p0 = tile * T;
-            // ---- stage the tile's coordinates -------------------------------------------------------------------
+            // ---- stage the tile's coordinates (and head adjoints) ----------------------------------------------------
             for (int e = tid; e < T; e += EPI_THREADS) {
                 int64_t gp = p0 + e;
                 if (gp >= a.n) gp = a.n - 1;
                 float x, y, z;
-                if (a.src.mode == 2) {
-                    int64_t g = a.src.grid_base + gp;
-                    int iz = (int)(g % a.src.nz);
-                    int64_t t2 = g / a.src.nz;
-                    int ix = (int)(t2 % a.src.nx);
-                    int iy = (int)(t2 / a.src.nx);
-                    x = __half2float(a.src.ax[ix]);
-                    y = __half2float(a.src.ay[iy]);
-                    z = __half2float(a.src.az[iz]);
-                } else {
-                    const float* xp = a.src.xyz + gp * a.src.xyz_stride;
-                    x = __ldg(xp);
-                    y = __ldg(xp + 1);
-                    z = (a.src.din > 2) ? __ldg(xp + 2) : 0.f;
-                }
+                point_coords(a.src, gp, x, y, z);
                 sXyz[e * 3] = x; sXyz[e * 3 + 1] = y; sXyz[e * 3 + 2] = z;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if constexpr (BWD) {
+                for (int e = tid; e < T * C; e += EPI_THREADS) {
+                    int64_t gp = p0 + e / C;
+                    sUbar[e] = (gp < a.n) ? __ldg(a.ubar + gp * C + (e % C)) : 0.f;
+                }
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
 
-            for (int l = 0; l <= Lh; ++l) {
-                if (l > 0) {
+            for (int j = 0; j <= Lh; ++j) {
+                const int l = BWD ? (Lh - j) : j;          // layer whose (pre-)activations this step touches
+                if (j > 0) {
                     mbar_wait(acc_ready, pa);
                     pa ^= 1;
                     tc_fence_after();
                 }
-                const bool last = (l == Lh);
-                for (int g = g0; g < T / 8; g += G::GSPLIT) {
-                    float part[C * 8];
-                    if (last) {
+                const bool last = (j == Lh);
+                float bsum = 0.f, wlsum = 0.f, w0s0 = 0.f, w0s1 = 0.f, w0s2 = 0.f;
+                float blv = 0.f;
+                if (!BWD && j > 0) blv = __ldg(a.bias30 + (l - 1) * H + u);
+
+                for (int g = gpart; g < G::NGRP; g += G::GS) {
+                    const int64_t pg = p0 + g * 4;               // first point of the group
+                    float acc[C][4];                              // TMEM / layer-0 values: fwd pre-activations, bwd incoming adjoint
+                    // ---------------- gather ----------------------------------------------------------------------------
+                    if (j > 0) {
 #pragma unroll
-                        for (int i = 0; i < C * 8; ++i) part[i] = 0.f;
+                        for (int c = 0; c < C; ++c) tmem_ld4(tmem_base + lane_base + mt * N + c * T + g * 4, acc[c]);
+                        tmem_ld_wait();
                     }
+                    float pre[C][4];                              // scaled pre-activations (30 z | 30 Z_k | 30 Q) of layer l
+                    if (!BWD) {
+                        if (j == 0) {
 #pragma unroll
-                    for (int ui = 0; ui < G::UPW; ++ui) {
-                        const int u = units[ui];
-                        const int mt = u >> 7;
-                        float acc[C][8];
-                        if (l == 0) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float* xp = sXyz + (g * 8 + i) * 3;
-                                float bz = b0[ui];
+                            for (int i = 0; i < 4; ++i) {
+                                const float* xp = sXyz + (g * 4 + i) * 3;
+                                float bz = w0v.w;
                                 if (a.src.shape_bias) {
-                                    int64_t gp = p0 + g * 8 + i;
-                                    if (gp >= a.n) gp = a.n - 1;
+                                    int64_t gp = pg + i < a.n ? pg + i : a.n - 1;
                                     bz = 30.f * __ldg(a.src.shape_bias + (gp / a.src.pps) * H + u);
                                 }
-                                acc[0][i] = fmaf(w0z[ui], xp[2], fmaf(w0y[ui], xp[1], fmaf(w0x[ui], xp[0], bz)));
+                                pre[0][i] = fmaf(w0v.z, xp[2], fmaf(w0v.y, xp[1], fmaf(w0v.x, xp[0], bz)));
                                 if constexpr (D > 0) {
-                                    acc[1][i] = w0x[ui];
-                                    if constexpr (D > 1) acc[2][i] = w0y[ui];
-                                    if constexpr (D > 2) acc[3][i] = w0z[ui];
-                                    if constexpr (LAP) acc[1 + D][i] = 0.f;
+                                    pre[1][i] = w0v.x;
+                                    if constexpr (D > 1) pre[2][i] = w0v.y;
+                                    if constexpr (D > 2) pre[3][i] = w0v.z;
+                                    if constexpr (LAP) pre[1 + D][i] = 0.f;
                                 }
                             }
                         } else {
 #pragma unroll
                             for (int c = 0; c < C; ++c)
-                                tmem_ld8(tmem_base + lane_base + mt * N + c * T + g * 8, acc[c]);
-                            tmem_ld_wait();
-                            float bl = __ldg(a.bias30 + (l - 1) * H + u);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) acc[0][i] += bl;
-                            if (a.planes) {
-                                // pre-activations for the reverse pass, unscaled: [l-1][c][point][unit]
-                                const float inv = 1.f / 30.f;
+                                for (int i = 0; i < 4; ++i) pre[c][i] = acc[c][i] + (c == 0 ? blv : 0.f);
+                            if (a.planes_t && pg < a.n_pad) {
+#pragma unroll
+                                for (int c = 0; c < C; ++c)
+                                    *reinterpret_cast<float4*>(a.planes_t + (((int64_t)(l - 1) * C + c) * H + u) * a.n_pad + pg) =
+                                        make_float4(pre[c][0], pre[c][1], pre[c][2], pre[c][3]);
+                            }
+                        }
+                    } else {
+                        if (j == 0) {
+#pragma unroll
+                            for (int c = 0; c < C; ++c)
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) acc[c][i] = sUbar[(g * 4 + i) * C + c] * wl;
+                        }
+                        if (l >= 1) {
+                            if (pg < a.n_pad) {
+#pragma unroll
+                                for (int c = 0; c < C; ++c) {
+                                    float4 v = __ldg(reinterpret_cast<const float4*>(
+                                        a.planes_t + (((int64_t)(l - 1) * C + c) * H + u) * a.n_pad + pg));
+                                    pre[c][0] = v.x; pre[c][1] = v.y; pre[c][2] = v.z; pre[c][3] = v.w;
+                                }
+                            } else {
 #pragma unroll
                                 for (int c = 0; c < C; ++c)
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        int64_t gp = p0 + g * 8 + i;
-                                        if (gp < a.n)
-                                            a.planes[((int64_t)(l - 1) * C + c) * ps + gp * H + u] = acc[c][i] * inv;
-                                    }
-                            }
-                        }
-                        // ---- jet activation, in place: acc[c][i] -> next-layer inputs --------------------------------
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float Zp[D > 0 ? D : 1], o[C];
-#pragma unroll
-                            for (int j = 0; j < D; ++j) Zp[j] = acc[1 + j][i];
-                            act_scaled<D, LAP>(acc[0][i], Zp, LAP ? acc[C - 1][i] : 0.f, o);
-#pragma unroll
-                            for (int c = 0; c < C; ++c) acc[c][i] = o[c];
-                        }
-                        if (!last) {
-                            // ---- next operand: row k = u, 8 consecutive columns = one 16 B chunk, SWIZZLE_128B --------
-                            const uint32_t rowoff = (uint32_t)(u >> 3) * G::SK + (uint32_t)(u & 7) * 128;
-#pragma unroll
-                            for (int c = 0; c < C; ++c) {
-                                const int ncol = c * T + g * 8;
-                                const uint32_t off = rowoff + (uint32_t)(ncol >> 6) * G::SN +
-                                                     ((((uint32_t)(ncol & 63) >> 3) ^ (uint32_t)(u & 7)) << 4);
-                                uint4 hi, lo;
-                                split2(acc[c][0], acc[c][1], hi.x, lo.x);
-                                split2(acc[c][2], acc[c][3], hi.y, lo.y);
-                                split2(acc[c][4], acc[c][5], hi.z, lo.z);
-                                split2(acc[c][6], acc[c][7], hi.w, lo.w);
-                                *reinterpret_cast<uint4*>(sB + off) = hi;
-                                if constexpr (PASSES == 3) *reinterpret_cast<uint4*>(sB + G::B_PART + off) = lo;
+                                    for (int i = 0; i < 4; ++i) pre[c][i] = 0.f;
                             }
                         } else {
 #pragma unroll
-                            for (int c = 0; c < C; ++c)
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) part[c * 8 + i] = fmaf(acc[c][i], wl[ui], part[c * 8 + i]);
-                        }
-                    }
-                    if (last) {
-                        warp_reduce_scatter<C * 8>(part, lane);
-                        // lane j holds value j of the first 32; lanes (j%8) hold value j of each trailing 8-block
-                        constexpr int FULL = (C * 8) / 32, REM = ((C * 8) % 32) / 8;
-#pragma unroll
-                        for (int b = 0; b < FULL; ++b) {
-                            int v = 32 * b + lane;
-                            sHead[slot * N + (v >> 3) * T + g * 8 + (v & 7)] = part[32 * b];
-                        }
-#pragma unroll
-                        for (int b = 0; b < REM; ++b) {
-                            if (lane < 8) {
-                                int v = 32 * FULL + 8 * b + lane;
-                                sHead[slot * N + (v >> 3) * T + g * 8 + (v & 7)] = part[32 * FULL + 8 * b];
+                            for (int i = 0; i < 4; ++i) {
+                                const float* xp = sXyz + (g * 4 + i) * 3;
+                                float bz = w0v.w;
+                                if (a.src.shape_bias) {
+                                    int64_t gp = pg + i < a.n ? pg + i : a.n - 1;
+                                    bz = 30.f * __ldg(a.src.shape_bias + (gp / a.src.pps) * H + u);
+                                }
+                                pre[0][i] = fmaf(w0v.z, xp[2], fmaf(w0v.y, xp[1], fmaf(w0v.x, xp[0], bz)));
+                                if constexpr (D > 0) {
+                                    pre[1][i] = w0v.x;
+                                    if constexpr (D > 1) pre[2][i] = w0v.y;
+                                    if constexpr (D > 2) pre[3][i] = w0v.z;
+                                    if constexpr (LAP) pre[1 + D][i] = 0.f;
+                                }
                             }
                         }
+                    }
+                    // ---------------- per-point jet math ----------------------------------------------------------------
+                    float out[C][4];      // fwd: layer outputs (h | A_k | P); bwd: scaled adjoints (zhat | Zhat_k | Qhat)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float s, c;
+                        sincos_reduced(pre[0][i], s, c);
+                        float S2 = 0.f;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) S2 = fmaf(pre[1 + k][i], pre[1 + k][i], S2);
+                        const float Qp = LAP ? pre[C - 1][i] : 0.f;
+                        if (!BWD) {
+                            out[0][i] = s;
+#pragma unroll
+                            for (int k = 0; k < D; ++k) out[1 + k][i] = c * pre[1 + k][i];
+                            if constexpr (LAP) out[C - 1][i] = fmaf(c, Qp, -s * S2);
+                        } else {
+                            const float Pb = LAP ? acc[C - 1][i] : 0.f;
+                            float ZA = 0.f;
+#pragma unroll
+                            for (int k = 0; k < D; ++k) ZA = fmaf(pre[1 + k][i], acc[1 + k][i], ZA);
+                            if (j == 0) {
+                                // dL/dw_last: ubar . (h | A_k | P) of the last sine layer
+                                const float* ubp = sUbar + (g * 4 + i) * C;
+                                float t = ubp[0] * s;
+#pragma unroll
+                                for (int k = 0; k < D; ++k) t = fmaf(ubp[1 + k], c * pre[1 + k][i], t);
+                                if constexpr (LAP) t = fmaf(ubp[C - 1], fmaf(c, Qp, -s * S2), t);
+                                wlsum += t;
+                            }
+                            float zh = c * acc[0][i] - s * ZA;
+                            if constexpr (LAP) zh -= Pb * fmaf(s, Qp, c * S2);
+                            out[0][i] = zh;
+#pragma unroll
+                            for (int k = 0; k < D; ++k) {
+                                float v = c * acc[1 + k][i];
+                                if constexpr (LAP) v -= 2.f * s * pre[1 + k][i] * Pb;
+                                out[1 + k][i] = v;
+                            }
+                            if constexpr (LAP) out[C - 1][i] = c * Pb;
+                        }
+                    }
+                    // ---------------- scatter ---------------------------------------------------------------------------
+                    if (BWD && l == 0) {
+                        // layer-0 parameter gradients: dW0[u][k] += 30 (zhat x_k + Zhat_k), db0[u] += 30 zhat
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float* xp = sXyz + (g * 4 + i) * 3;
+                            bsum += out[0][i];
+                            if constexpr (D > 0) w0s0 += fmaf(out[0][i], xp[0], out[1][i]);
+                            if constexpr (D > 1) w0s1 += fmaf(out[0][i], xp[1], out[2][i]);
+                            if constexpr (D > 2) w0s2 += fmaf(out[0][i], xp[2], out[3][i]);
+                            if (a.sb_grad && pg + i < a.n)
+                                atomicAdd(a.sb_grad + ((pg + i) / a.src.pps) * H + u, 30.f * out[0][i]);
+                        }
+                    } else if (!BWD && last) {
+                        float part[P2];
+#pragma unroll
+                        for (int v = 0; v < P2; ++v) part[v] = (v < C * 4) ? out[v >> 2][v & 3] * wl : 0.f;
+                        warp_reduce_scatter<P2>(part, lane);
+                        if (lane < C * 4) sHead[ub * N + (lane >> 2) * T + g * 4 + (lane & 3)] = part[0];
+                    } else {
+                        if (BWD) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) bsum += out[0][i];
+                        }
+                        __nv_bfloat16* gdst = BWD ? a.GT : a.actT;
+                        const int li = BWD ? (l - 1) : l;        // layer slot in GT / actT
+                        const bool gstore = (gdst != nullptr) && (pg < a.n_pad);
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const int ncol = c * T + g * 4;
+                            const uint32_t off = rowoff + (uint32_t)(ncol >> 6) * G::SN +
+                                                 ((((uint32_t)(ncol & 63) >> 3) ^ (uint32_t)(u & 7)) << 4) +
+                                                 (uint32_t)(ncol & 4) * 2;
+                            uint2 hi, lo;
+                            split2(out[c][0], out[c][1], hi.x, lo.x);
+                            split2(out[c][2], out[c][3], hi.y, lo.y);
+                            *reinterpret_cast<uint2*>(sB + off) = hi;
+                            if constexpr (PASSES == 3) *reinterpret_cast<uint2*>(sB + G::B_PART + off) = lo;
+                            if (gstore) {
+                                if (!BWD && pg + 3 >= a.n) {   // forward tail: points >= n must be exact zeros in actT
+                                    float o0 = pg + 0 < a.n ? out[c][0] : 0.f, o1 = pg + 1 < a.n ? out[c][1] : 0.f;
+                                    float o2 = pg + 2 < a.n ? out[c][2] : 0.f, o3 = pg + 3 < a.n ? out[c][3] : 0.f;
+                                    split2(o0, o1, hi.x, lo.x);
+                                    split2(o2, o3, hi.y, lo.y);
+                                }
+                                __nv_bfloat16* row = gdst + ((int64_t)(li * 2) * H + u) * rowlen + (int64_t)c * a.n_pad + pg;
+                                *reinterpret_cast<uint2*>(row) = hi;
+                                *reinterpret_cast<uint2*>(row + (int64_t)H * rowlen) = lo;
+                            }
+                        }
+                    }
+                }
+                // ---------------- end of step -----------------------------------------------------------------------------
+                if (BWD) {
+                    if (j == 0) atomicAdd(a.dw_last + u, wlsum);
+                    if (l >= 1) {
+                        atomicAdd(a.db[l] + u, 30.f * bsum);
+                    } else {
+                        if (!a.sb_grad) atomicAdd(a.db[0] + u, 30.f * bsum);
+                        if constexpr (D > 0) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 0, 30.f * w0s0);
+                        if constexpr (D > 1) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 1, 30.f * w0s1);
+                        if constexpr (D > 2) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 2, 30.f * w0s2);
                     }
                 }
                 if (!last) {
@@ -415,75 +486,83 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_forward(const __grid_constan
                     mbar_arrive(b_ready);
                 }
             }
-            // ---- last layer sum over units + output head -------------------------------------------------------------
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int e = tid; e < T; e += EPI_THREADS) {
-                int64_t gp = p0 + e;
-                if (gp < a.n) {
-                    float v[C];
+            if constexpr (!BWD) {
+                // ---- last layer: sum the per-unit-block partials, apply the output head ------------------------------
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                for (int e = tid; e < T; e += EPI_THREADS) {
+                    int64_t gp = p0 + e;
+                    if (gp < a.n) {
+                        float v[C];
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        float s = 0.f;
+                        for (int c = 0; c < C; ++c) {
+                            float s = 0.f;
 #pragma unroll
-                        for (int w = 0; w < G::NSLOT; ++w) s += sHead[w * N + c * T + e];
-                        v[c] = s;
-                    }
-                    float u = v[0] + __ldg(a.b_last);
-                    if (a.head_saved) {
-                        a.head_saved[gp * C] = u;
-#pragma unroll
-                        for (int c = 1; c < C; ++c) a.head_saved[gp * C + c] = v[c];
-                    }
-                    if (a.head == DIGS_HEAD_IDENTITY) {
-                        a.f[gp] = u;
-                        if constexpr (D > 0) {
-#pragma unroll
-                            for (int j = 0; j < D; ++j) a.grad[gp * D + j] = v[1 + j];
-                            if constexpr (LAP) a.lap[gp] = v[1 + D];
+                            for (int w = 0; w < G::NUB; ++w) s += sHead[w * N + c * T + e];
+                            v[c] = s;
                         }
-                    } else {
-                        float aa = fabsf(u) + 1e-8f;
-                        float sg = (u > 0.f) ? 1.f : ((u < 0.f) ? -1.f : 0.f);
-                        float ra = sqrtf(aa);
-                        a.f[gp] = a.scale * (sg * ra - a.radius);
-                        if constexpr (D > 0) {
-                            float g1 = 0.5f / ra, gg = 0.f;
+                        float uu = v[0] + __ldg(a.b_last);
+                        if (a.head_saved) {
+                            a.head_saved[gp * C] = uu;
 #pragma unroll
-                            for (int j = 0; j < D; ++j) {
-                                a.grad[gp * D + j] = a.scale * g1 * v[1 + j];
-                                gg = fmaf(v[1 + j], v[1 + j], gg);
+                            for (int c = 1; c < C; ++c) a.head_saved[gp * C + c] = v[c];
+                        }
+                        if (a.head == DIGS_HEAD_IDENTITY) {
+                            a.f[gp] = uu;
+                            if constexpr (D > 0) {
+#pragma unroll
+                                for (int k = 0; k < D; ++k) a.grad[gp * D + k] = v[1 + k];
+                                if constexpr (LAP) a.lap[gp] = v[1 + D];
                             }
-                            if constexpr (LAP) {
-                                float g2 = -0.25f * sg / (aa * ra);
-                                a.lap[gp] = a.scale * (g1 * v[1 + D] + g2 * gg);
+                        } else {
+                            float aa = fabsf(uu) + 1e-8f;
+                            float sg = (uu > 0.f) ? 1.f : ((uu < 0.f) ? -1.f : 0.f);
+                            float ra = sqrtf(aa);
+                            a.f[gp] = a.scale * (sg * ra - a.radius);
+                            if constexpr (D > 0) {
+                                float g1 = 0.5f / ra, gg = 0.f;
+#pragma unroll
+                                for (int k = 0; k < D; ++k) {
+                                    a.grad[gp * D + k] = a.scale * g1 * v[1 + k];
+                                    gg = fmaf(v[1 + k], v[1 + k], gg);
+                                }
+                                if constexpr (LAP) {
+                                    float g2 = -0.25f * sg / (aa * ra);
+                                    a.lap[gp] = a.scale * (g1 * v[1 + D] + g2 * gg);
+                                }
                             }
                         }
                     }
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");   // sXyz / sHead are rewritten by the next tile
+            asm volatile("bar.sync 1, 512;" ::: "memory");   // sXyz / sHead / sUbar are rewritten by the next tile
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc<G::TMEM_COLS>(tmem_base);
+    if (warp == EPI_WARPS + 1) tmem_dealloc<G::TMEM_COLS>(tmem_base);
 }
 
-// ---- weight preparation: 30*W -> bf16 hi/lo, 30*b, 30*W0 -----------------------------------------------------------
+// ---- weight preparation: 30*W (forward operand) and (30*W)^T (reverse operand) as bf16 hi/lo; 30*b; 30*W0 ---------
 struct PrepPtrs {
     const float* W[DIGS_MAX_LAYERS];
     const float* b[DIGS_MAX_LAYERS];
 };
-__global__ void k_tc_prep(PrepPtrs p, int Lh, int H, int d, int w0_stride, __nv_bfloat16* Whl /*[2][Lh*H][H]*/,
-                          float* bias30 /*[Lh][H]*/, float* w0_30 /*[H][4]*/) {
+// Wq layout: [4][Lh][H][H] bf16 with slot 0 = hi, 1 = lo, 2 = hi transposed, 3 = lo transposed
+__global__ void k_tc_prep(PrepPtrs p, int Lh, int H, int d, int w0_stride, __nv_bfloat16* Wq, float* bias30, float* w0_30) {
     const int64_t per = (int64_t)H * H;
     const int64_t total = (int64_t)Lh * per;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         int l = (int)(e / per);
-        float w = 30.f * p.W[1 + l][e - (int64_t)l * per];
+        int64_t r = e - (int64_t)l * per;
+        int u = (int)(r / H), k = (int)(r % H);
+        float w = 30.f * p.W[1 + l][r];
         __nv_bfloat16 hi = __float2bfloat16_rn(w);
-        Whl[e] = hi;
-        Whl[total + e] = __float2bfloat16_rn(w - __bfloat162float(hi));
+        __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+        Wq[e] = hi;
+        Wq[total + e] = lo;
+        int64_t et = (int64_t)l * per + (int64_t)k * H + u;
+        Wq[2 * total + et] = hi;
+        Wq[3 * total + et] = lo;
     }
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < Lh * H) bias30[i] = 30.f * p.b[1 + i / H][i % H];
@@ -497,10 +576,7 @@ __global__ void k_tc_prep(PrepPtrs p, int Lh, int H, int d, int w0_stride, __nv_
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeFn get_encode() {
+EncodeFn get_encode() {
     static EncodeFn fn = nullptr;
     if (!fn) {
         cudaDriverEntryPointQueryResult q;
@@ -514,12 +590,30 @@ static EncodeFn get_encode() {
 
 bool supported(const DigsNet* net) { return net->H == 256 || net->H == 128 || net->H == 512; }
 
-static size_t whl_bytes(const DigsNet* net) { return align_up((size_t)2 * net->Lh * net->H * net->H * 2, 256); }
+static size_t wq_bytes(const DigsNet* net) { return align_up((size_t)4 * net->Lh * net->H * net->H * 2, 256); }
 static size_t bias_bytes(const DigsNet* net) { return align_up((size_t)net->Lh * net->H * 4, 256); }
 static size_t w0_bytes(const DigsNet* net) { return align_up((size_t)net->H * 16, 256); }
-size_t prep_ws_bytes(const DigsNet* net) { return whl_bytes(net) + bias_bytes(net) + w0_bytes(net); }
+size_t prep_ws_bytes(const DigsNet* net) { return wq_bytes(net) + bias_bytes(net) + w0_bytes(net); }
 
-static int num_sms() {
+SavedLayout saved_layout(const DigsNet* net, int64_t n, int want_lap) {
+    SavedLayout s;
+    s.C = 1 + net->d + (want_lap ? 1 : 0);
+    s.n_pad = (n + 7) / 8 * 8;
+    s.planes_bytes = align_up((size_t)net->Lh * s.C * net->H * s.n_pad * 4, 256);
+    s.act_bytes = align_up((size_t)net->Lh * 2 * net->H * s.C * s.n_pad * 2, 256);
+    s.head_bytes = align_up((size_t)n * s.C * 4, 256);
+    return s;
+}
+size_t saved_bytes(const DigsNet* net, int64_t n, int want_lap) {
+    SavedLayout s = saved_layout(net, n, want_lap);
+    return s.planes_bytes + s.act_bytes + s.head_bytes;
+}
+size_t bwd_ws_bytes(const DigsNet* net, int64_t n, int want_lap) {
+    SavedLayout s = saved_layout(net, n, want_lap);
+    return prep_ws_bytes(net) + s.act_bytes /* GT */ + s.head_bytes /* ubar */;
+}
+
+int num_sms() {
     static int n = 0;
     if (!n) {
         int dev = 0;
@@ -529,14 +623,14 @@ static int num_sms() {
     return n;
 }
 
-template <int D, int LAP, int H, int PASSES>
+template <int D, int LAP, int H, int PASSES, bool BWD>
 static int launch(const CUtensorMap& tmap, const Args& a, cudaStream_t st) {
     using G = Cfg<D, LAP, H, PASSES>;
-    auto kern = k_tc_forward<D, LAP, H, PASSES>;
+    auto kern = k_tc_net<D, LAP, H, PASSES, BWD>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("tc forward: smem attribute (%d B): %s", G::SMEM_BYTES, cudaGetErrorString(e)); return DIGS_ECUDA; }
+        if (e != cudaSuccess) { set_error("tc net: smem attribute (%d B): %s", G::SMEM_BYTES, cudaGetErrorString(e)); return DIGS_ECUDA; }
         attr_set = true;
     }
     int64_t tiles = (a.n + G::T - 1) / G::T;
@@ -544,60 +638,121 @@ static int launch(const CUtensorMap& tmap, const Args& a, cudaStream_t st) {
     kern<<<grid, NTHREADS, G::SMEM_BYTES, st>>>(tmap, a);
     count_launch();
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error("tc forward launch: %s", cudaGetErrorString(e)); return DIGS_ECUDA; }
+    if (e != cudaSuccess) { set_error("tc net launch: %s", cudaGetErrorString(e)); return DIGS_ECUDA; }
     return DIGS_OK;
 }
 
-template <int D, int LAP, int PASSES>
+template <int D, int LAP, int PASSES, bool BWD>
 static int launch_h(const DigsNet* net, const CUtensorMap& tmap, const Args& a, cudaStream_t st) {
     switch (net->H) {
-        case 128: return launch<D, LAP, 128, PASSES>(tmap, a, st);
-        case 256: return launch<D, LAP, 256, PASSES>(tmap, a, st);
-        case 512: return launch<D, LAP, 512, PASSES>(tmap, a, st);
+        case 128: return launch<D, LAP, 128, PASSES, BWD>(tmap, a, st);
+        case 256: return launch<D, LAP, 256, PASSES, BWD>(tmap, a, st);
+        case 512: return launch<D, LAP, 512, PASSES, BWD>(tmap, a, st);
     }
-    set_error("tc forward: H=%d not supported (128, 256, 512)", net->H);
+    set_error("tc net: H=%d not supported (128, 256, 512)", net->H);
     return DIGS_ENOTIMPL;
 }
 
-// Forward jet / value query on the tensor cores.  want_jet = 0 -> value channel only (C = 1).
-int forward(const DigsNet* net, const PreSrc& src, int64_t n, int want_jet, int want_lap, float* f, float* grad,
-            float* lap, float* planes, float* head_saved, void* ws, int passes, cudaStream_t st) {
-    if (n == 0) return DIGS_OK;
+template <bool BWD>
+static int dispatch(const DigsNet* net, const CUtensorMap& tmap, const Args& a, int want_jet, int want_lap, int passes,
+                    cudaStream_t st) {
+    if (!want_jet) {
+        if constexpr (BWD) { set_error("tc reverse needs jet channels"); return DIGS_EINVAL; }
+        else return (passes == 3) ? launch_h<0, 0, 3, false>(net, tmap, a, st) : launch_h<0, 0, 1, false>(net, tmap, a, st);
+    }
+    if (net->d == 3 && want_lap) return (passes == 3) ? launch_h<3, 1, 3, BWD>(net, tmap, a, st) : launch_h<3, 1, 1, BWD>(net, tmap, a, st);
+    if (net->d == 3) return (passes == 3) ? launch_h<3, 0, 3, BWD>(net, tmap, a, st) : launch_h<3, 0, 1, BWD>(net, tmap, a, st);
+    if (want_lap) return (passes == 3) ? launch_h<2, 1, 3, BWD>(net, tmap, a, st) : launch_h<2, 1, 1, BWD>(net, tmap, a, st);
+    return (passes == 3) ? launch_h<2, 0, 3, BWD>(net, tmap, a, st) : launch_h<2, 0, 1, BWD>(net, tmap, a, st);
+}
+
+// prepares the weight operands in `ws` and encodes the TMA map over them
+static int prepare(const DigsNet* net, void* ws, CUtensorMap* tmap, Args* a, cudaStream_t st) {
     EncodeFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return DIGS_ECUDA; }
     char* w = reinterpret_cast<char*>(ws);
-    __nv_bfloat16* Whl = reinterpret_cast<__nv_bfloat16*>(w);
-    float* bias30 = reinterpret_cast<float*>(w + whl_bytes(net));
-    float* w0_30 = reinterpret_cast<float*>(w + whl_bytes(net) + bias_bytes(net));
+    __nv_bfloat16* Wq = reinterpret_cast<__nv_bfloat16*>(w);
+    float* bias30 = reinterpret_cast<float*>(w + wq_bytes(net));
+    float* w0_30 = reinterpret_cast<float*>(w + wq_bytes(net) + bias_bytes(net));
     PrepPtrs pp;
     for (int l = 0; l <= net->Lh + 1; ++l) { pp.W[l] = net->W[l]; pp.b[l] = net->b[l]; }
-    k_tc_prep<<<148 * 4, 256, 0, st>>>(pp, net->Lh, net->H, net->d, net->w0_stride, Whl, bias30, w0_30);
+    k_tc_prep<<<148 * 4, 256, 0, st>>>(pp, net->Lh, net->H, net->d, net->w0_stride, Wq, bias30, w0_30);
     count_launch();
-    CUtensorMap tmap;
-    cuuint64_t gdim[2] = {(cuuint64_t)net->H, (cuuint64_t)2 * net->Lh * net->H};
+    cuuint64_t gdim[2] = {(cuuint64_t)net->H, (cuuint64_t)4 * net->Lh * net->H};
     cuuint64_t gstr[1] = {(cuuint64_t)net->H * 2};
     cuuint32_t box[2] = {64, 128};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Whl, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Wq, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DIGS_ECUDA; }
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed (%d)", (int)r); return DIGS_ECUDA; }
+    a->Lh = net->Lh;
+    a->w0_30 = w0_30;
+    a->bias30 = bias30;
+    a->w_last = net->W[net->Lh + 1];
+    a->b_last = net->b[net->Lh + 1];
+    a->head = net->head;
+    a->radius = net->radius;
+    a->scale = net->scale;
+    return DIGS_OK;
+}
+
+// Forward jet / value query.  want_jet = 0 -> value channel only (C = 1).  saved: NULL or saved_bytes() bytes.
+int forward(const DigsNet* net, const PreSrc& src, int64_t n, int want_jet, int want_lap, float* f, float* grad,
+            float* lap, void* saved, void* ws, int passes, cudaStream_t st) {
+    if (n == 0) return DIGS_OK;
+    CUtensorMap tmap;
     Args a{};
+    int rc = prepare(net, ws, &tmap, &a, st);
+    if (rc) return rc;
     a.src = src;
     a.n = n;
-    a.Lh = net->Lh;
-    a.w0_30 = w0_30;
-    a.bias30 = bias30;
-    a.w_last = net->W[net->Lh + 1];
-    a.b_last = net->b[net->Lh + 1];
-    a.head = net->head;
-    a.radius = net->radius;
-    a.scale = net->scale;
-    a.f = f; a.grad = grad; a.lap = lap; a.planes = planes; a.head_saved = head_saved;
-    if (!want_jet) return (passes == 3) ? launch_h<0, 0, 3>(net, tmap, a, st) : launch_h<0, 0, 1>(net, tmap, a, st);
-    if (net->d == 3 && want_lap) return (passes == 3) ? launch_h<3, 1, 3>(net, tmap, a, st) : launch_h<3, 1, 1>(net, tmap, a, st);
-    if (net->d == 3) return (passes == 3) ? launch_h<3, 0, 3>(net, tmap, a, st) : launch_h<3, 0, 1>(net, tmap, a, st);
-    if (want_lap) return (passes == 3) ? launch_h<2, 1, 3>(net, tmap, a, st) : launch_h<2, 1, 1>(net, tmap, a, st);
-    return (passes == 3) ? launch_h<2, 0, 3>(net, tmap, a, st) : launch_h<2, 0, 1>(net, tmap, a, st);
+    a.f = f; a.grad = grad; a.lap = lap;
+    if (saved) {
+        SavedLayout s = saved_layout(net, n, want_lap);
+        char* sp = reinterpret_cast<char*>(saved);
+        a.n_pad = s.n_pad;
+        a.planes_t = reinterpret_cast<float*>(sp);
+        a.actT = reinterpret_cast<__nv_bfloat16*>(sp + s.planes_bytes);
+        a.head_saved = reinterpret_cast<float*>(sp + s.planes_bytes + s.act_bytes);
+    } else {
+        a.n_pad = (n + 7) / 8 * 8;
+    }
+    return dispatch<false>(net, tmap, a, want_jet, want_lap, passes, st);
+}
+
+// Reverse pass: head adjoint (fp32 kernel) -> fused dgrad kernel (bias / layer-0 / last-layer gradients, GT) -> wgrad GEMMs.
+int backward(const DigsNet* net, const PreSrc& src, int64_t n, int want_lap, const float* f_bar, const float* g_bar,
+             const float* l_bar, const void* saved, void* ws, const DigsGrads* grads, float* sb_grad, int passes,
+             cudaStream_t st) {
+    if (n == 0) return DIGS_OK;
+    SavedLayout s = saved_layout(net, n, want_lap);
+    const char* sp = reinterpret_cast<const char*>(saved);
+    float* planes_t = reinterpret_cast<float*>(const_cast<char*>(sp));
+    __nv_bfloat16* actT = reinterpret_cast<__nv_bfloat16*>(const_cast<char*>(sp) + s.planes_bytes);
+    const float* head_saved = reinterpret_cast<const float*>(sp + s.planes_bytes + s.act_bytes);
+    char* w = reinterpret_cast<char*>(ws);
+    __nv_bfloat16* GT = reinterpret_cast<__nv_bfloat16*>(w + prep_ws_bytes(net));
+    float* ubar = reinterpret_cast<float*>(w + prep_ws_bytes(net) + s.act_bytes);
+    int rc = simt::head_seed(net, n, want_lap, head_saved, f_bar, g_bar, l_bar, ubar, grads->db[net->Lh + 1], st);
+    if (rc) return rc;
+    CUtensorMap tmap;
+    Args a{};
+    rc = prepare(net, ws, &tmap, &a, st);
+    if (rc) return rc;
+    a.src = src;
+    a.n = n;
+    a.n_pad = s.n_pad;
+    a.planes_t = planes_t;
+    a.ubar = ubar;
+    a.GT = GT;
+    for (int l = 0; l <= net->Lh; ++l) a.db[l] = grads->db[l];
+    a.dW0 = grads->dW[0];
+    a.w0_stride = net->w0_stride;
+    a.dw_last = grads->dW[net->Lh + 1];
+    a.sb_grad = sb_grad;
+    rc = dispatch<true>(net, tmap, a, 1, want_lap, passes, st);
+    if (rc) return rc;
+    return wgrad(net, GT, actT, s.C, s.n_pad, grads, passes, st);
 }
 
 }  // namespace tcpath

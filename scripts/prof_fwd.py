@@ -1,0 +1,20 @@
+"""Profiling driver (GPU): a few forward-jet launches of the C2 off-surface cloud + one 128^3 grid query."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import digs_b200
+from digs_b200 import jet as djet, _lib
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "bf16x2"
+torch.manual_seed(3627473)
+net = digs_b200.DiGSNetwork(0, 3, 256, "sine", "none", 4, "mfgi", [1.6, 0.1], precision=mode).cuda()
+fc = net.decoder.fc_block
+params = [p.detach() for p in fc.flat_params()]
+xyz = (torch.rand(15000, 3, device="cuda") * 2.2 - 1.1)
+for _ in range(4):
+    djet.jet_forward_raw(fc.spec(), params, xyz, None, 0, True, True, fc.mode())
+axes, _, _ = digs_b200.grid_axes(128, np.array([[-1, 1], [-1, 1], [-1, 1]], dtype=float))
+for _ in range(2):
+    digs_b200.grid_query(net, axes)
+torch.cuda.synchronize()
+print("ok")
