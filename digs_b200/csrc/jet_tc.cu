@@ -22,10 +22,11 @@
 // Layer 0 (K = d) and the last layer (N = 1) are fp32 FMAs / warp reductions from registers.
 //
 // What the forward leaves in `saved` for the reverse pass (per cloud, n_pad = n rounded up to 8):
-//   planes_t [Lh][C][H][n_pad] fp32   pre-activations scaled by 30: (30 z | 30 Z_k | 30 Q), point-contiguous
-//   actT     [Lh][2][H][C*n_pad] bf16 layer inputs (h | A_k | P) of layers 1..Lh as hi/lo rows = wgrad operand
-//   head     [n][C] fp32              (u | gu_k | lu)
-// and the reverse kernel writes GT [Lh][2][H][C*n_pad] bf16 = adjoints (zbar | Zbar_k | Qbar)/30, the other wgrad operand.
+//   planes   [Lh][C][n_pad][H] fp32    pre-activations scaled by 30: (30 z | 30 Z_k | 30 Q)
+//   actP     [Lh][C*n_pad][H]  uint32  layer inputs (h | A_k | P) of layers 1..Lh as (bf16 hi | bf16 lo << 16) = wgrad operand
+//   head     [n][C] fp32               (u | gu_k | lu)
+// and the reverse kernel writes GP [Lh][C*n_pad][H] uint32 = adjoints (zbar | Zbar_k | Qbar)/30, the other wgrad operand.
+// Every global access of an epilogue warp covers 32 consecutive units of one (channel, point): one 128-byte line.
 //
 // Warp roles (576 threads): warps 0-15 epilogue, warp 16 TMA producer, warp 17 MMA issuer + TMEM owner.
 #include "digs_internal.h"
@@ -262,7 +263,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
         uint32_t pa = 0;
         const float4 w0v = __ldg(reinterpret_cast<const float4*>(a.w0_30) + u);
         const float wl = __ldg(a.w_last + u);
-        const int64_t rowlen = (int64_t)C * a.n_pad;     // row length of actT / GT
         const uint32_t rowoff = (uint32_t)(u >> 3) * G::SK + (uint32_t)(u & 7) * 128;
 
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -328,11 +328,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                             for (int c = 0; c < C; ++c)
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) pre[c][i] = acc[c][i] + (c == 0 ? blv : 0.f);
-                            if (a.planes_t && pg < a.n_pad) {
+                            if (a.planes_t) {
+                                // [l-1][c][point][unit]: a warp stores 32 consecutive units = one 128 B line
 #pragma unroll
-                                for (int c = 0; c < C; ++c)
-                                    *reinterpret_cast<float4*>(a.planes_t + (((int64_t)(l - 1) * C + c) * H + u) * a.n_pad + pg) =
-                                        make_float4(pre[c][0], pre[c][1], pre[c][2], pre[c][3]);
+                                for (int c = 0; c < C; ++c) {
+                                    float* dst = a.planes_t + (((int64_t)(l - 1) * C + c) * a.n_pad + pg) * H + u;
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i)
+                                        if (pg + i < a.n_pad) dst[i * H] = pre[c][i];
+                                }
                             }
                         }
                     } else {
@@ -343,18 +347,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                                 for (int i = 0; i < 4; ++i) acc[c][i] = sUbar[(g * 4 + i) * C + c] * wl;
                         }
                         if (l >= 1) {
-                            if (pg < a.n_pad) {
 #pragma unroll
-                                for (int c = 0; c < C; ++c) {
-                                    float4 v = __ldg(reinterpret_cast<const float4*>(
-                                        a.planes_t + (((int64_t)(l - 1) * C + c) * H + u) * a.n_pad + pg));
-                                    pre[c][0] = v.x; pre[c][1] = v.y; pre[c][2] = v.z; pre[c][3] = v.w;
-                                }
-                            } else {
+                            for (int c = 0; c < C; ++c) {
+                                const float* srcp = a.planes_t + (((int64_t)(l - 1) * C + c) * a.n_pad + pg) * H + u;
 #pragma unroll
-                                for (int c = 0; c < C; ++c)
-#pragma unroll
-                                    for (int i = 0; i < 4; ++i) pre[c][i] = 0.f;
+                                for (int i = 0; i < 4; ++i) pre[c][i] = (pg + i < a.n_pad) ? __ldg(srcp + i * H) : 0.f;
                             }
                         } else {
 #pragma unroll
@@ -440,9 +437,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
 #pragma unroll
                             for (int i = 0; i < 4; ++i) bsum += out[0][i];
                         }
-                        __nv_bfloat16* gdst = BWD ? a.GT : a.actT;
-                        const int li = BWD ? (l - 1) : l;        // layer slot in GT / actT
-                        const bool gstore = (gdst != nullptr) && (pg < a.n_pad);
+                        uint32_t* gdst = reinterpret_cast<uint32_t*>(BWD ? a.GT : a.actT);
+                        const int li = BWD ? (l - 1) : l;        // layer slot in GP / actP
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
                             const int ncol = c * T + g * 4;
@@ -454,16 +450,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                             split2(out[c][2], out[c][3], hi.y, lo.y);
                             *reinterpret_cast<uint2*>(sB + off) = hi;
                             if constexpr (PASSES == 3) *reinterpret_cast<uint2*>(sB + G::B_PART + off) = lo;
-                            if (gstore) {
-                                if (!BWD && pg + 3 >= a.n) {   // forward tail: points >= n must be exact zeros in actT
-                                    float o0 = pg + 0 < a.n ? out[c][0] : 0.f, o1 = pg + 1 < a.n ? out[c][1] : 0.f;
-                                    float o2 = pg + 2 < a.n ? out[c][2] : 0.f, o3 = pg + 3 < a.n ? out[c][3] : 0.f;
-                                    split2(o0, o1, hi.x, lo.x);
-                                    split2(o2, o3, hi.y, lo.y);
+                            if (gdst) {
+                                // wgrad operand, [slot][channel*n_pad + point][unit] words of (hi | lo << 16); a warp stores
+                                // 32 consecutive units = one 128 B line.  Forward tail points (>= n) must be exact zeros.
+                                uint32_t* dst = gdst + (((int64_t)li * C + c) * a.n_pad + pg) * H + u;
+                                uint32_t w0 = __byte_perm(hi.x, lo.x, 0x5410), w1 = __byte_perm(hi.x, lo.x, 0x7632);
+                                uint32_t w2 = __byte_perm(hi.y, lo.y, 0x5410), w3 = __byte_perm(hi.y, lo.y, 0x7632);
+                                if (!BWD) {
+                                    if (pg + 0 >= a.n) w0 = 0;
+                                    if (pg + 1 >= a.n) w1 = 0;
+                                    if (pg + 2 >= a.n) w2 = 0;
+                                    if (pg + 3 >= a.n) w3 = 0;
                                 }
-                                __nv_bfloat16* row = gdst + ((int64_t)(li * 2) * H + u) * rowlen + (int64_t)c * a.n_pad + pg;
-                                *reinterpret_cast<uint2*>(row) = hi;
-                                *reinterpret_cast<uint2*>(row + (int64_t)H * rowlen) = lo;
+                                if (pg + 0 < a.n_pad) dst[0] = w0;
+                                if (pg + 1 < a.n_pad) dst[H] = w1;
+                                if (pg + 2 < a.n_pad) dst[2 * H] = w2;
+                                if (pg + 3 < a.n_pad) dst[3 * H] = w3;
                             }
                         }
                     }

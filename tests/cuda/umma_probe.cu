@@ -17,6 +17,7 @@ struct Cfg {
     uint32_t b_sk;    // MN-major layout: byte stride between 8-deep k groups
     uint32_t b_lbo;   // descriptor fields for B
     uint32_t b_sbo;
+    int a_mn;         // A MN-major (layout sn=8192, sk=1024, descriptor LBO=8192 SBO=1024)
 };
 
 __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap tmapA, const __nv_bfloat16* A,
@@ -38,7 +39,14 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
     for (int i = tid; i < 32768 / 4; i += 128) ((uint32_t*)sB)[i] = 0;
     __syncthreads();
     // ---- A: K-major SW128: row m at m*128 B, 16B chunk j stored at chunk (j ^ (m & 7))
-    if (!cfg.a_tma) {
+    if (cfg.a_mn) {
+        for (int e = tid; e < M * K; e += 128) {
+            int m = e / K, k = e % K;
+            int m_lo = m & 63, m_hi = m >> 6, k_lo = k & 7, k_hi = k >> 3;
+            uint32_t off = m_hi * 8192 + k_hi * 1024 + k_lo * 128 + ((((m_lo >> 3) ^ k_lo)) << 4) + (m_lo & 7) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(sA + off) = A[m * K + k];
+        }
+    } else if (!cfg.a_tma) {
         for (int e = tid; e < M * 8; e += 128) {
             int m = e >> 3, j = e & 7;
             uint4 v = *reinterpret_cast<const uint4*>(A + m * K + j * 8);
@@ -73,9 +81,10 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
             mbar_wait(&bar_tma, 0);
         }
         tc_fence_after();
-        const uint32_t idesc = make_idesc_bf16(M, N, 0, cfg.b_mn);
+        const uint32_t idesc = make_idesc_bf16(M, N, cfg.a_mn, cfg.b_mn);
         for (int kk = 0; kk < K / 16; ++kk) {
-            uint64_t da = make_smem_desc(smem_u32(sA) + kk * 32, 16, 1024, LAYOUT_SW128);
+            uint64_t da = cfg.a_mn ? make_smem_desc(smem_u32(sA) + kk * 2048, 8192, 1024, LAYOUT_SW128)
+                                   : make_smem_desc(smem_u32(sA) + kk * 32, 16, 1024, LAYOUT_SW128);
             uint64_t db;
             if (!cfg.b_mn) db = make_smem_desc(smem_u32(sB) + kk * 32, 16, 1024, LAYOUT_SW128);
             else db = make_smem_desc(smem_u32(sB) + kk * 2 * cfg.b_sk, cfg.b_lbo, cfg.b_sbo, LAYOUT_SW128);
@@ -136,7 +145,9 @@ int main() {
         {"B MN-major sn=8192 sk=1024, desc LBO=sk SBO=sn", {0, 1, 8192, 1024, 1024, 8192}},
         {"B MN-major sn=1024 sk=2048, desc LBO=sn SBO=sk", {0, 1, 1024, 2048, 1024, 2048}},
         {"B MN-major sn=1024 sk=2048, desc LBO=sk SBO=sn", {0, 1, 1024, 2048, 2048, 1024}},
-        {"A TMA, B MN-major sn=8192 sk=1024, LBO=sn SBO=sk", {1, 1, 8192, 1024, 8192, 1024}},
+        {"A TMA, B MN-major sn=8192 sk=1024, LBO=sn SBO=sk", {1, 1, 8192, 1024, 8192, 1024, 0}},
+        {"A MN-major, B K-major", {0, 0, 0, 0, 0, 0, 1}},
+        {"A MN-major, B MN-major sn=8192 sk=1024", {0, 1, 8192, 1024, 8192, 1024, 1}},
     };
     for (auto& t : tests) {
         cudaMemset(dD, 0xff, M * N * 4);
