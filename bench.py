@@ -178,6 +178,7 @@ def run_ours(args, rank, world, local_rank):
     crit = digs_b200.DiGSLoss(**copy.deepcopy(LOSS_KW))
     crit.global_counts = (N_POINTS * world, N_POINTS * world)
     flat = ddist.FlatGrads(list(net.parameters()), extra=8)
+    net.decoder.fc_block.accumulate_grads_in_place = True   # reverse kernels add straight into the flat buffer
     L = _lib.lib()
     n_batches = args.steps + args.warmup
     hb = [tuple(t.pin_memory() for t in b) for b in host_batches(n_batches, seed=rank + 1)]

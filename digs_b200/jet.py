@@ -136,6 +136,10 @@ class JetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz, shape_bias, spec, pts_per_shape, want_lap, mode, *params):
+        ctx.grad_targets = None
+        if getattr(spec, "accumulate_in_place", False) and all(
+                p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 for p in params):
+            ctx.grad_targets = [p.grad for p in params]
         params = [p.detach() for p in params]
         xyz_d = xyz.detach()
         sb = None if shape_bias is None else shape_bias.detach().contiguous()
@@ -165,8 +169,13 @@ class JetFunction(torch.autograd.Function):
         fb = None if f_bar is None else f_bar.contiguous()
         gb = None if g_bar is None else g_bar.contiguous()
         lb = None if l_bar is None else l_bar.contiguous()
+        # Accumulate straight into already-materialised .grad buffers (e.g. the views of dist.FlatGrads) when the caller
+        # opted in: the kernels add with atomics anyway, so this removes a zero-fill and an add per parameter.
+        direct = ctx.grad_targets
         grads, sb_grad = jet_backward_raw(ctx.spec, params, xyz, sb, ctx.pps, ctx.want_lap, fb, gb, lb, saved,
-                                          ctx.mode)
+                                          ctx.mode, grad_out=direct)
+        if direct is not None:
+            grads = [None] * len(params)
         xyz_grad = None
         if ctx.needs_input_grad[0]:
             if gb is not None or lb is not None:

@@ -137,6 +137,10 @@ class FCBlock(nn.Module):
         self.net = nn.Sequential(*blocks)
         _INITS[init_type]([blk[0] for blk in self.net])
         self.precision = "fp32"
+        # When True and every parameter already has a contiguous fp32 .grad (e.g. digs_b200.dist.FlatGrads views), the
+        # reverse kernels add into those buffers directly and autograd receives None for the parameters (the same
+        # contract as fused weight-gradient accumulation in large-model trainers).  Off by default: plain autograd.
+        self.accumulate_grads_in_place = False
 
     # -- description handed to the kernels -------------------------------------------------------
     def linears(self):
@@ -152,8 +156,10 @@ class FCBlock(nn.Module):
         lins = self.linears()
         head = _lib.HEAD_SQRT if self.init_type in _SQRT_HEAD_INITS else _lib.HEAD_IDENTITY
         radius, scale = self.sphere_init_params
-        return NetSpec(self.spatial_dim, lins[0].out_features, len(lins) - 2, head, radius, scale,
+        spec = NetSpec(self.spatial_dim, lins[0].out_features, len(lins) - 2, head, radius, scale,
                        lins[0].in_features)
+        spec.accumulate_in_place = self.accumulate_grads_in_place
+        return spec
 
     def mode(self):
         return _lib.MODES[self.precision]
