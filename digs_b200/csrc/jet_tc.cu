@@ -6,7 +6,7 @@
 // models/losses.py:72-76,100-106), the chunk loop of utils.implicit2mesh (utils/utils.py:343-348), and the
 // network part of loss.backward() (train_surface_reconstruction.py:128).
 //
-// One persistent CTA per SM walks point tiles.  A tile is T points x C jet channels = N <= 128 operand columns
+// One persistent CTA per SM walks point tiles.  A tile is T points x C jet channels <= 128 operand columns
 // (column = channel*T + point).  Every hidden layer is evaluated TRANSPOSED on the tensor cores:
 //
 //   forward   D[unit][col]   = sum_k (30 W_l)[unit][k]  * X[col][k]        A = 30 W_l      (K-major,  TMA ring)
@@ -21,6 +21,9 @@
 // DIGS_MODE_BF16X2 runs three MMA passes per product (hi*hi + hi*lo + lo*hi); DIGS_MODE_BF16 runs hi*hi only.
 // Layer 0 (K = d) and the last layer (N = 1) are fp32 FMAs / warp reductions from registers.
 //
+// The kernel is written for NCTX tile contexts per CTA (own operand buffer, TMEM columns and epilogue warps, the MMA
+// warp alternating between them); measurements chose NCTX = 1 with 128-column tiles (see Cfg).
+//
 // What the forward leaves in `saved` for the reverse pass (per cloud, n_pad = n rounded up to 8):
 //   planes   [Lh][C][n_pad][H] fp32    pre-activations scaled by 30: (30 z | 30 Z_k | 30 Q)
 //   actP     [Lh][C*n_pad][H]  uint32  layer inputs (h | A_k | P) of layers 1..Lh as (bf16 hi | bf16 lo << 16) = wgrad operand
@@ -32,6 +35,7 @@
 #include "digs_internal.h"
 #include "tc_common.cuh"
 #include <cuda.h>
+#include <type_traits>
 
 namespace digs {
 namespace tcpath {
@@ -39,8 +43,7 @@ namespace tcpath {
 using namespace digs::tc;
 
 constexpr int EPI_WARPS = 16;
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int NTHREADS = EPI_THREADS + 64;
+constexpr int NTHREADS = EPI_WARPS * 32 + 64;
 constexpr int STAGES = 5;
 constexpr int STAGE_BYTES = 128 * 64 * 2;  // one A tile: 128 rows x 64 k, bf16
 
@@ -48,28 +51,38 @@ template <int D, int LAP, int H_, int PASSES>
 struct Cfg {
     static constexpr int C = 1 + D + LAP;
     static constexpr int H = H_;
-    static constexpr int N = (H_ > 256) ? 64 : 128;   // UMMA N (operand columns); 64 keeps X in shared memory at H=512
-    static constexpr int T = (N / C) / 8 * 8;         // points per tile
-    static constexpr int NGRP = T / 4;                // 4-point groups
+    // Tile contexts in flight per CTA.  Two 64-column contexts ping-ponging on the MMA warp were measured SLOWER than one
+    // 128-column context: a tcgen05.mma with N = 64 re-reads the 4 KB A tile from shared memory for half the math, and
+    // the operand fetch (not the tensor pipe) becomes the limit.  The code keeps the context machinery; NCTX stays 1.
+    static constexpr int NCTX = 1;
+    static constexpr int N = (H_ > 256) ? 64 : 128;   // UMMA N = operand columns per context (64 keeps X in smem at H=512)
+    static constexpr int T = (N / C) / 4 * 4;         // points per tile (whole 4-point groups)
+    static constexpr int NGRP = T / 4;
     static constexpr int MT = H / 128;                // UMMA M tiles
     static constexpr int NG = N / 64;                 // 64-column groups of the MN-major operand
     static constexpr int SN = 1024;                   // byte stride between column groups   (descriptor LBO)
     static constexpr int SK = NG * 1024;              // byte stride between 8-deep k groups (descriptor SBO)
     static constexpr int B_PART = (H / 8) * SK;       // bytes of one operand part (hi or lo)
     static constexpr int NPARTS = (PASSES == 3) ? 2 : 1;
+    static constexpr int CTX_BYTES = B_PART * NPARTS;
     static constexpr int KSLABS = H / 64;
-    static constexpr int TMEM_COLS = (MT * N <= 128) ? 128 : ((MT * N <= 256) ? 256 : 512);
+    static constexpr int CTX_COLS = MT * N;           // TMEM columns per context
+    static constexpr int TMEM_COLS = (NCTX * CTX_COLS <= 128) ? 128 : ((NCTX * CTX_COLS <= 256) ? 256 : 512);
+    static constexpr int EW = EPI_WARPS / NCTX;       // epilogue warps per context
+    static constexpr int ETHREADS = EW * 32;
     static constexpr int NUB = H / 32;                // 32-unit blocks
-    static constexpr int GS = EPI_WARPS / NUB;        // epilogue warps sharing one unit block (split over point groups)
-    static constexpr int OFF_RING = B_PART * NPARTS;
-    static constexpr int OFF_XYZ = OFF_RING + STAGES * STAGE_BYTES;
-    static constexpr int OFF_HEAD = OFF_XYZ + 128 * 3 * 4;
-    static constexpr int OFF_UBAR = OFF_HEAD + NUB * N * 4;
-    static constexpr int OFF_BAR = OFF_UBAR + N * 4;
-    static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
+    static constexpr int GS = EW / NUB;               // epilogue warps sharing one unit block (split over point groups)
+    static constexpr int GITER = (NGRP + GS - 1) / GS;
+    static constexpr int OFF_RING = NCTX * CTX_BYTES;
+    static constexpr int OFF_XYZ = OFF_RING + STAGES * STAGE_BYTES;      // [NCTX][N*3] floats
+    static constexpr int OFF_HEAD = OFF_XYZ + NCTX * N * 3 * 4;           // [NCTX][NUB][N] floats
+    static constexpr int OFF_UBAR = OFF_HEAD + NCTX * NUB * N * 4;        // [NCTX][N] floats
+    static constexpr int OFF_BAR = OFF_UBAR + NCTX * N * 4;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;               // + alignment slack
     static_assert(H == 128 || H == 256 || H == 512, "H must be 128, 256 or 512");
-    static_assert(MT * N <= 512, "accumulators exceed TMEM");
-    static_assert(EPI_WARPS % NUB == 0, "unit blocks must divide the epilogue warps");
+    static_assert(NCTX * CTX_COLS <= 512, "accumulators exceed TMEM");
+    static_assert(EW % NUB == 0, "unit blocks must divide the epilogue warps of a context");
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 struct Args {
@@ -86,10 +99,10 @@ struct Args {
     float* grad;
     float* lap;
     float* planes_t;          // forward: written (or NULL); reverse: read
-    __nv_bfloat16* actT;      // forward: written (or NULL)
+    __nv_bfloat16* actT;      // forward: written (or NULL)  (actP words)
     float* head_saved;        // forward: written (or NULL)
     const float* ubar;        // reverse: [n][C] head adjoints (u_bar | gu_bar_k | lu_bar)
-    __nv_bfloat16* GT;        // reverse: written
+    __nv_bfloat16* GT;        // reverse: written (GP words)
     float* db[DIGS_MAX_LAYERS];  // reverse: bias gradients, layers 0..Lh (accumulated)
     float* dW0;               // reverse: (H, w0_stride), first d columns accumulated
     int w0_stride;
@@ -145,41 +158,41 @@ __device__ __forceinline__ void point_coords(const PreSrc& s, int64_t gp, float&
     }
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 template <int D, int LAP, int H, int PASSES, bool BWD>
 __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ CUtensorMap tmapW, Args a) {
     using G = Cfg<D, LAP, H, PASSES>;
-    constexpr int C = G::C, T = G::T, N = G::N, MT = G::MT;
+    constexpr int C = G::C, T = G::T, N = G::N, MT = G::MT, NCTX = G::NCTX;
     constexpr int P2 = (C * 4 <= 4) ? 4 : ((C * 4 <= 16) ? 16 : 32);   // padded size of the head partial-sum vector
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sB = smem;
     uint8_t* sRing = smem + G::OFF_RING;
-    float* sXyz = reinterpret_cast<float*>(smem + G::OFF_XYZ);
-    float* sHead = reinterpret_cast<float*>(smem + G::OFF_HEAD);
-    float* sUbar = reinterpret_cast<float*>(smem + G::OFF_UBAR);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
-    uint64_t* w_full = bars;                      // [STAGES]
-    uint64_t* w_empty = bars + STAGES;            // [STAGES]
-    uint64_t* b_ready = bars + 2 * STAGES;        // epilogue -> MMA: next operand complete (512 arrivals)
-    uint64_t* acc_ready = bars + 2 * STAGES + 1;  // MMA -> epilogue: accumulators complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+    uint64_t* w_full = bars;                          // [STAGES]
+    uint64_t* w_empty = bars + STAGES;                // [STAGES]
+    uint64_t* b_ready = bars + 2 * STAGES;            // [NCTX] epilogue -> MMA: next operand complete (ETHREADS arrivals)
+    uint64_t* acc_ready = bars + 2 * STAGES + NCTX;   // [NCTX] MMA -> epilogue: accumulators complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NCTX);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        mbar_init(b_ready, EPI_THREADS);
-        mbar_init(acc_ready, 1);
+        for (int i = 0; i < NCTX; ++i) { mbar_init(&b_ready[i], G::ETHREADS); mbar_init(&acc_ready[i], 1); }
         fence_barrier_init();
         tma_prefetch_desc(&tmapW);
     }
     if (warp == EPI_WARPS + 1) tmem_alloc<G::TMEM_COLS>(tmem_slot);
-    for (int i = tid; i < G::OFF_RING / 16; i += NTHREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < G::OFF_RING / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int64_t num_tiles = (a.n + T - 1) / T;
+    const int64_t num_tiles = (a.n_pad + T - 1) / T;   // tiles cover [0, n_pad): the wgrad operands have no unwritten column
+    const int64_t num_rounds = (num_tiles + NCTX - 1) / NCTX;   // a round = NCTX consecutive tiles
     const int Lh = a.Lh;
 
     if (warp == EPI_WARPS) {
@@ -187,88 +200,105 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+            for (int64_t r = blockIdx.x; r < num_rounds; r += gridDim.x)
                 for (int j = 0; j < Lh; ++j) {
                     const int l = BWD ? (Lh - j) : (j + 1);
-                    for (int ks = 0; ks < G::KSLABS; ++ks)
-                        for (int m = 0; m < MT; ++m)
-                            for (int part = 0; part < G::NPARTS; ++part) {
-                                mbar_wait(&w_empty[stage], phase ^ 1);
-                                mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
-                                // rows: [dir = fwd|transposed][part = hi|lo][layer][H]
-                                tma_load_2d(sRing + stage * STAGE_BYTES, &tmapW, &w_full[stage], ks * 64,
-                                            (((BWD ? 2 : 0) + part) * Lh + (l - 1)) * H + m * 128);
-                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                            }
+                    for (int ctx = 0; ctx < NCTX; ++ctx) {
+                        if (r * NCTX + ctx >= num_tiles) continue;
+                        for (int ks = 0; ks < G::KSLABS; ++ks)
+                            for (int m = 0; m < MT; ++m)
+                                for (int part = 0; part < G::NPARTS; ++part) {
+                                    mbar_wait(&w_empty[stage], phase ^ 1);
+                                    mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
+                                    // rows: [dir = fwd|transposed][part = hi|lo][layer][H]
+                                    tma_load_2d(sRing + stage * STAGE_BYTES, &tmapW, &w_full[stage], ks * 64,
+                                                (((BWD ? 2 : 0) + part) * Lh + (l - 1)) * H + m * 128);
+                                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                                }
+                    }
                 }
         }
     } else if (warp == EPI_WARPS + 1) {
-        // ================= MMA issuer ============================================================================
+        // ================= MMA issuer: alternates between the tile contexts ========================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, N, /*A K-major*/ 0, /*B MN-major*/ 1);
-            const uint32_t sB_hi = smem_u32(sB), sB_lo = smem_u32(sB) + G::B_PART;
             int stage = 0;
-            uint32_t phase = 0, pb = 0;
-            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
-                for (int j = 0; j < Lh; ++j) {
-                    mbar_wait(b_ready, pb);
-                    pb ^= 1;
-                    tc_fence_after();
-                    for (int ks = 0; ks < G::KSLABS; ++ks)
-                        for (int m = 0; m < MT; ++m) {
-                            const uint32_t d_tmem = tmem_base + m * N;
-                            mbar_wait(&w_full[stage], phase);   // A_hi tile: hi*hi (+ hi*lo)
-                            tc_fence_after();
-                            {
-                                const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) {
-                                    uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
-                                    uint32_t koff = (ks * 8 + kk * 2) * G::SK;
-                                    uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
-                                    umma_bf16(d_tmem, da, db, idesc, (ks | kk) != 0);
-                                    if constexpr (PASSES == 3) {
-                                        uint64_t dbl = make_smem_desc(sB_lo + koff, G::SN, G::SK, LAYOUT_SW128);
-                                        umma_bf16(d_tmem, da, dbl, idesc, 1);
-                                    }
-                                }
-                            }
-                            umma_commit(&w_empty[stage]);
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                            if constexpr (PASSES == 3) {
-                                mbar_wait(&w_full[stage], phase);   // A_lo tile: lo*hi
+            uint32_t phase = 0, pb[2] = {0, 0};
+            for (int64_t r = blockIdx.x; r < num_rounds; r += gridDim.x)
+                for (int j = 0; j < Lh; ++j)
+                    for (int ctx = 0; ctx < NCTX; ++ctx) {
+                        if (r * NCTX + ctx >= num_tiles) continue;
+                        const uint32_t sB_hi = smem_u32(smem) + ctx * G::CTX_BYTES, sB_lo = sB_hi + G::B_PART;
+                        mbar_wait(&b_ready[ctx], pb[ctx]);
+                        pb[ctx] ^= 1;
+                        tc_fence_after();
+                        for (int ks = 0; ks < G::KSLABS; ++ks)
+                            for (int m = 0; m < MT; ++m) {
+                                const uint32_t d_tmem = tmem_base + ctx * G::CTX_COLS + m * N;
+                                mbar_wait(&w_full[stage], phase);   // A_hi tile: hi*hi (+ hi*lo)
                                 tc_fence_after();
-                                const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
+                                {
+                                    const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
 #pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) {
-                                    uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
-                                    uint32_t koff = (ks * 8 + kk * 2) * G::SK;
-                                    uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
-                                    umma_bf16(d_tmem, da, db, idesc, 1);
+                                    for (int kk = 0; kk < 4; ++kk) {
+                                        uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
+                                        uint32_t koff = (ks * 8 + kk * 2) * G::SK;
+                                        uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
+                                        umma_bf16(d_tmem, da, db, idesc, (ks | kk) != 0);
+                                        if constexpr (PASSES == 3) {
+                                            uint64_t dbl = make_smem_desc(sB_lo + koff, G::SN, G::SK, LAYOUT_SW128);
+                                            umma_bf16(d_tmem, da, dbl, idesc, 1);
+                                        }
+                                    }
                                 }
                                 umma_commit(&w_empty[stage]);
                                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                                if constexpr (PASSES == 3) {
+                                    mbar_wait(&w_full[stage], phase);   // A_lo tile: lo*hi
+                                    tc_fence_after();
+                                    const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk) {
+                                        uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
+                                        uint32_t koff = (ks * 8 + kk * 2) * G::SK;
+                                        uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
+                                        umma_bf16(d_tmem, da, db, idesc, 1);
+                                    }
+                                    umma_commit(&w_empty[stage]);
+                                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                                }
                             }
-                        }
-                    umma_commit(acc_ready);
-                }
+                        umma_commit(&acc_ready[ctx]);
+                    }
         }
     } else {
-        // ================= epilogue warps 0..15 ==================================================================
-        const int ub = warp % G::NUB;          // 32-unit block; ub % 4 == warp % 4 = TMEM lane quarter of this warp
-        const int gpart = warp / G::NUB;       // which share of the point groups
-        const int u = ub * 32 + lane;          // unit index
+        // ================= epilogue warps: 8 (H <= 256) or 16 per context ============================================
+        const int ctx = warp / G::EW;
+        const int wl = warp % G::EW;               // warp index within the context's group
+        const int etid = tid - ctx * G::ETHREADS;  // thread index within the group
+        const int ub = wl % G::NUB;                // 32-unit block; ub % 4 == warp % 4 = TMEM lane quarter of this warp
+        const int gpart = wl / G::NUB;             // which share of the point groups
+        const int u = ub * 32 + lane;              // unit index
         const int mt = ub >> 2;
-        const uint32_t lane_base = (uint32_t)((ub & 3) * 32) << 16;
+        const uint32_t t_base = tmem_base + ((uint32_t)((ub & 3) * 32) << 16) + ctx * G::CTX_COLS + mt * N;
+        uint8_t* sB = smem + ctx * G::CTX_BYTES;
+        float* sXyz = reinterpret_cast<float*>(smem + G::OFF_XYZ) + ctx * N * 3;
+        float* sHead = reinterpret_cast<float*>(smem + G::OFF_HEAD) + ctx * G::NUB * N;
+        float* sUbar = reinterpret_cast<float*>(smem + G::OFF_UBAR) + ctx * N;
         uint32_t pa = 0;
         const float4 w0v = __ldg(reinterpret_cast<const float4*>(a.w0_30) + u);
-        const float wl = __ldg(a.w_last + u);
+        const float wl_u = __ldg(a.w_last + u);
         const uint32_t rowoff = (uint32_t)(u >> 3) * G::SK + (uint32_t)(u & 7) * 128;
+        const uint32_t usw = (uint32_t)(u & 7) << 4;
+        const int64_t plane_stride = a.n_pad * (int64_t)H;     // one (layer, channel) plane of `planes` / actP / GP
 
-        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int64_t r = blockIdx.x; r < num_rounds; r += gridDim.x) {
+            const int64_t tile = r * NCTX + ctx;
+            if (tile >= num_tiles) continue;       // whole group skips together (producer / MMA skip it too)
             const int64_t p0 = tile * T;
+            const bool full = (p0 + T <= a.n);     // no tail handling needed anywhere in this tile
             // ---- stage the tile's coordinates (and head adjoints) ----------------------------------------------------
-            for (int e = tid; e < T; e += EPI_THREADS) {
+            for (int e = etid; e < T; e += G::ETHREADS) {
                 int64_t gp = p0 + e;
                 if (gp >= a.n) gp = a.n - 1;
                 float x, y, z;
@@ -276,37 +306,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                 sXyz[e * 3] = x; sXyz[e * 3 + 1] = y; sXyz[e * 3 + 2] = z;
             }
             if constexpr (BWD) {
-                for (int e = tid; e < T * C; e += EPI_THREADS) {
+                for (int e = etid; e < T * C; e += G::ETHREADS) {
                     int64_t gp = p0 + e / C;
                     sUbar[e] = (gp < a.n) ? __ldg(a.ubar + gp * C + (e % C)) : 0.f;
                 }
             }
-            asm volatile("bar.sync 1, 512;" ::: "memory");
+            named_bar_sync(1 + ctx, G::ETHREADS);
+            // per-tile base pointers of this thread's unit column (point p0 + 4*gpart, channel 0, layer slot 0)
+            float* pl_tile = a.planes_t ? a.planes_t + (p0 + gpart * 4) * H + u : nullptr;
+            uint32_t* gp_tile = nullptr;
+            {
+                __nv_bfloat16* gq = BWD ? a.GT : a.actT;
+                if (gq) gp_tile = reinterpret_cast<uint32_t*>(gq) + (p0 + gpart * 4) * H + u;
+            }
 
-            for (int j = 0; j <= Lh; ++j) {
-                const int l = BWD ? (Lh - j) : j;          // layer whose (pre-)activations this step touches
-                if (j > 0) {
-                    mbar_wait(acc_ready, pa);
-                    pa ^= 1;
-                    tc_fence_after();
-                }
-                const bool last = (j == Lh);
-                float bsum = 0.f, wlsum = 0.f, w0s0 = 0.f, w0s1 = 0.f, w0s2 = 0.f;
-                float blv = 0.f;
-                if (!BWD && j > 0) blv = __ldg(a.bias30 + (l - 1) * H + u);
-
-                for (int g = gpart; g < G::NGRP; g += G::GS) {
-                    const int64_t pg = p0 + g * 4;               // first point of the group
-                    float acc[C][4];                              // TMEM / layer-0 values: fwd pre-activations, bwd incoming adjoint
-                    // ---------------- gather ----------------------------------------------------------------------------
+            auto run_tile = [&](auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
+                for (int j = 0; j <= Lh; ++j) {
+                    const int l = BWD ? (Lh - j) : j;          // layer whose (pre-)activations this step touches
                     if (j > 0) {
-#pragma unroll
-                        for (int c = 0; c < C; ++c) tmem_ld4(tmem_base + lane_base + mt * N + c * T + g * 4, acc[c]);
-                        tmem_ld_wait();
+                        mbar_wait(&acc_ready[ctx], pa);
+                        pa ^= 1;
+                        tc_fence_after();
                     }
-                    float pre[C][4];                              // scaled pre-activations (30 z | 30 Z_k | 30 Q) of layer l
-                    if (!BWD) {
-                        if (j == 0) {
+                    const bool last = (j == Lh);
+                    float bsum = 0.f, wlsum = 0.f, w0s0 = 0.f, w0s1 = 0.f, w0s2 = 0.f;
+                    float blv = 0.f;
+                    if (!BWD && j > 0) blv = __ldg(a.bias30 + (l - 1) * H + u);
+                    // layer slot bases: planes slot = l-1 (both directions); GP slot = l-1 (reverse), actP slot = l (forward)
+                    float* pl_l = pl_tile ? pl_tile + (int64_t)(l - 1) * C * plane_stride : nullptr;
+                    uint32_t* gp_l = gp_tile ? gp_tile + (int64_t)(BWD ? (l - 1) : l) * C * plane_stride : nullptr;
+
+#pragma unroll
+                    for (int gi = 0; gi < G::GITER; ++gi) {
+                        const int g = gpart + gi * G::GS;
+                        if (G::GS > 1 && g >= G::NGRP) break;
+                        const int64_t pg = p0 + g * 4;               // first point of the group
+                        const int goff = gi * G::GS * 4 * H;         // element offset of this group from the tile base pointers
+                        float acc[C][4];                              // TMEM values: fwd pre-activations, bwd incoming adjoint
+                        if (j > 0) {
+#pragma unroll
+                            for (int c = 0; c < C; ++c) tmem_ld4(t_base + c * T + g * 4, acc[c]);
+                            tmem_ld_wait();
+                        }
+                        float pre[C][4];                              // scaled pre-activations (30 z | 30 Z_k | 30 Q) of layer l
+                        if ((!BWD && j == 0) || (BWD && l == 0)) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const float* xp = sXyz + (g * 4 + i) * 3;
@@ -323,175 +367,159 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                                     if constexpr (LAP) pre[1 + D][i] = 0.f;
                                 }
                             }
-                        } else {
+                        } else if (!BWD) {
 #pragma unroll
                             for (int c = 0; c < C; ++c)
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) pre[c][i] = acc[c][i] + (c == 0 ? blv : 0.f);
-                            if (a.planes_t) {
-                                // [l-1][c][point][unit]: a warp stores 32 consecutive units = one 128 B line
+                            if (pl_l) {
 #pragma unroll
                                 for (int c = 0; c < C; ++c) {
-                                    float* dst = a.planes_t + (((int64_t)(l - 1) * C + c) * a.n_pad + pg) * H + u;
+                                    float* dst = pl_l + c * plane_stride + goff;
 #pragma unroll
                                     for (int i = 0; i < 4; ++i)
-                                        if (pg + i < a.n_pad) dst[i * H] = pre[c][i];
+                                        if (FULL || pg + i < a.n_pad) dst[i * H] = pre[c][i];
                                 }
                             }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < C; ++c) {
+                                const float* srcp = pl_l + c * plane_stride + goff;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    pre[c][i] = (FULL || pg + i < a.n_pad) ? __ldg(srcp + i * H) : 0.f;
+                            }
                         }
-                    } else {
-                        if (j == 0) {
+                        if (BWD && j == 0) {
 #pragma unroll
                             for (int c = 0; c < C; ++c)
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) acc[c][i] = sUbar[(g * 4 + i) * C + c] * wl;
+                                for (int i = 0; i < 4; ++i) acc[c][i] = sUbar[(g * 4 + i) * C + c] * wl_u;
                         }
-                        if (l >= 1) {
+                        // ---------------- per-point jet math ------------------------------------------------------------
+                        float out[C][4];   // fwd: layer outputs (h | A_k | P); bwd: scaled adjoints (zhat | Zhat_k | Qhat)
 #pragma unroll
-                            for (int c = 0; c < C; ++c) {
-                                const float* srcp = a.planes_t + (((int64_t)(l - 1) * C + c) * a.n_pad + pg) * H + u;
+                        for (int i = 0; i < 4; ++i) {
+                            float s, c;
+                            sincos_reduced(pre[0][i], s, c);
+                            float S2 = 0.f;
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) pre[c][i] = (pg + i < a.n_pad) ? __ldg(srcp + i * H) : 0.f;
+                            for (int k = 0; k < D; ++k) S2 = fmaf(pre[1 + k][i], pre[1 + k][i], S2);
+                            const float Qp = LAP ? pre[C - 1][i] : 0.f;
+                            if (!BWD) {
+                                out[0][i] = s;
+#pragma unroll
+                                for (int k = 0; k < D; ++k) out[1 + k][i] = c * pre[1 + k][i];
+                                if constexpr (LAP) out[C - 1][i] = fmaf(c, Qp, -s * S2);
+                            } else {
+                                const float Pb = LAP ? acc[C - 1][i] : 0.f;
+                                float ZA = 0.f;
+#pragma unroll
+                                for (int k = 0; k < D; ++k) ZA = fmaf(pre[1 + k][i], acc[1 + k][i], ZA);
+                                if (j == 0) {
+                                    // dL/dw_last: ubar . (h | A_k | P) of the last sine layer
+                                    const float* ubp = sUbar + (g * 4 + i) * C;
+                                    float t = ubp[0] * s;
+#pragma unroll
+                                    for (int k = 0; k < D; ++k) t = fmaf(ubp[1 + k], c * pre[1 + k][i], t);
+                                    if constexpr (LAP) t = fmaf(ubp[C - 1], fmaf(c, Qp, -s * S2), t);
+                                    wlsum += t;
+                                }
+                                float zh = c * acc[0][i] - s * ZA;
+                                if constexpr (LAP) zh -= Pb * fmaf(s, Qp, c * S2);
+                                out[0][i] = zh;
+#pragma unroll
+                                for (int k = 0; k < D; ++k) {
+                                    float v = c * acc[1 + k][i];
+                                    if constexpr (LAP) v -= 2.f * s * pre[1 + k][i] * Pb;
+                                    out[1 + k][i] = v;
+                                }
+                                if constexpr (LAP) out[C - 1][i] = c * Pb;
                             }
-                        } else {
+                        }
+                        // ---------------- scatter -----------------------------------------------------------------------
+                        if (BWD && l == 0) {
+                            // layer-0 parameter gradients: dW0[u][k] += 30 (zhat x_k + Zhat_k), db0[u] += 30 zhat
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const float* xp = sXyz + (g * 4 + i) * 3;
-                                float bz = w0v.w;
-                                if (a.src.shape_bias) {
-                                    int64_t gp = pg + i < a.n ? pg + i : a.n - 1;
-                                    bz = 30.f * __ldg(a.src.shape_bias + (gp / a.src.pps) * H + u);
-                                }
-                                pre[0][i] = fmaf(w0v.z, xp[2], fmaf(w0v.y, xp[1], fmaf(w0v.x, xp[0], bz)));
-                                if constexpr (D > 0) {
-                                    pre[1][i] = w0v.x;
-                                    if constexpr (D > 1) pre[2][i] = w0v.y;
-                                    if constexpr (D > 2) pre[3][i] = w0v.z;
-                                    if constexpr (LAP) pre[1 + D][i] = 0.f;
-                                }
+                                bsum += out[0][i];
+                                if constexpr (D > 0) w0s0 += fmaf(out[0][i], xp[0], out[1][i]);
+                                if constexpr (D > 1) w0s1 += fmaf(out[0][i], xp[1], out[2][i]);
+                                if constexpr (D > 2) w0s2 += fmaf(out[0][i], xp[2], out[3][i]);
+                                if (a.sb_grad && pg + i < a.n)
+                                    atomicAdd(a.sb_grad + ((pg + i) / a.src.pps) * H + u, 30.f * out[0][i]);
                             }
-                        }
-                    }
-                    // ---------------- per-point jet math ----------------------------------------------------------------
-                    float out[C][4];      // fwd: layer outputs (h | A_k | P); bwd: scaled adjoints (zhat | Zhat_k | Qhat)
+                        } else if (!BWD && last) {
+                            float part[P2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float s, c;
-                        sincos_reduced(pre[0][i], s, c);
-                        float S2 = 0.f;
-#pragma unroll
-                        for (int k = 0; k < D; ++k) S2 = fmaf(pre[1 + k][i], pre[1 + k][i], S2);
-                        const float Qp = LAP ? pre[C - 1][i] : 0.f;
-                        if (!BWD) {
-                            out[0][i] = s;
-#pragma unroll
-                            for (int k = 0; k < D; ++k) out[1 + k][i] = c * pre[1 + k][i];
-                            if constexpr (LAP) out[C - 1][i] = fmaf(c, Qp, -s * S2);
+                            for (int v = 0; v < P2; ++v) part[v] = (v < C * 4) ? out[v >> 2][v & 3] * wl_u : 0.f;
+                            warp_reduce_scatter<P2>(part, lane);
+                            if (lane < C * 4) sHead[ub * N + (lane >> 2) * T + g * 4 + (lane & 3)] = part[0];
                         } else {
-                            const float Pb = LAP ? acc[C - 1][i] : 0.f;
-                            float ZA = 0.f;
+                            if (BWD) {
 #pragma unroll
-                            for (int k = 0; k < D; ++k) ZA = fmaf(pre[1 + k][i], acc[1 + k][i], ZA);
-                            if (j == 0) {
-                                // dL/dw_last: ubar . (h | A_k | P) of the last sine layer
-                                const float* ubp = sUbar + (g * 4 + i) * C;
-                                float t = ubp[0] * s;
-#pragma unroll
-                                for (int k = 0; k < D; ++k) t = fmaf(ubp[1 + k], c * pre[1 + k][i], t);
-                                if constexpr (LAP) t = fmaf(ubp[C - 1], fmaf(c, Qp, -s * S2), t);
-                                wlsum += t;
+                                for (int i = 0; i < 4; ++i) bsum += out[0][i];
                             }
-                            float zh = c * acc[0][i] - s * ZA;
-                            if constexpr (LAP) zh -= Pb * fmaf(s, Qp, c * S2);
-                            out[0][i] = zh;
 #pragma unroll
-                            for (int k = 0; k < D; ++k) {
-                                float v = c * acc[1 + k][i];
-                                if constexpr (LAP) v -= 2.f * s * pre[1 + k][i] * Pb;
-                                out[1 + k][i] = v;
-                            }
-                            if constexpr (LAP) out[C - 1][i] = c * Pb;
-                        }
-                    }
-                    // ---------------- scatter ---------------------------------------------------------------------------
-                    if (BWD && l == 0) {
-                        // layer-0 parameter gradients: dW0[u][k] += 30 (zhat x_k + Zhat_k), db0[u] += 30 zhat
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float* xp = sXyz + (g * 4 + i) * 3;
-                            bsum += out[0][i];
-                            if constexpr (D > 0) w0s0 += fmaf(out[0][i], xp[0], out[1][i]);
-                            if constexpr (D > 1) w0s1 += fmaf(out[0][i], xp[1], out[2][i]);
-                            if constexpr (D > 2) w0s2 += fmaf(out[0][i], xp[2], out[3][i]);
-                            if (a.sb_grad && pg + i < a.n)
-                                atomicAdd(a.sb_grad + ((pg + i) / a.src.pps) * H + u, 30.f * out[0][i]);
-                        }
-                    } else if (!BWD && last) {
-                        float part[P2];
-#pragma unroll
-                        for (int v = 0; v < P2; ++v) part[v] = (v < C * 4) ? out[v >> 2][v & 3] * wl : 0.f;
-                        warp_reduce_scatter<P2>(part, lane);
-                        if (lane < C * 4) sHead[ub * N + (lane >> 2) * T + g * 4 + (lane & 3)] = part[0];
-                    } else {
-                        if (BWD) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) bsum += out[0][i];
-                        }
-                        uint32_t* gdst = reinterpret_cast<uint32_t*>(BWD ? a.GT : a.actT);
-                        const int li = BWD ? (l - 1) : l;        // layer slot in GP / actP
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const int ncol = c * T + g * 4;
-                            const uint32_t off = rowoff + (uint32_t)(ncol >> 6) * G::SN +
-                                                 ((((uint32_t)(ncol & 63) >> 3) ^ (uint32_t)(u & 7)) << 4) +
-                                                 (uint32_t)(ncol & 4) * 2;
-                            uint2 hi, lo;
-                            split2(out[c][0], out[c][1], hi.x, lo.x);
-                            split2(out[c][2], out[c][3], hi.y, lo.y);
-                            *reinterpret_cast<uint2*>(sB + off) = hi;
-                            if constexpr (PASSES == 3) *reinterpret_cast<uint2*>(sB + G::B_PART + off) = lo;
-                            if (gdst) {
-                                // wgrad operand, [slot][channel*n_pad + point][unit] words of (hi | lo << 16); a warp stores
-                                // 32 consecutive units = one 128 B line.  Forward tail points (>= n) must be exact zeros.
-                                uint32_t* dst = gdst + (((int64_t)li * C + c) * a.n_pad + pg) * H + u;
-                                uint32_t w0 = __byte_perm(hi.x, lo.x, 0x5410), w1 = __byte_perm(hi.x, lo.x, 0x7632);
-                                uint32_t w2 = __byte_perm(hi.y, lo.y, 0x5410), w3 = __byte_perm(hi.y, lo.y, 0x7632);
-                                if (!BWD) {
-                                    if (pg + 0 >= a.n) w0 = 0;
-                                    if (pg + 1 >= a.n) w1 = 0;
-                                    if (pg + 2 >= a.n) w2 = 0;
-                                    if (pg + 3 >= a.n) w3 = 0;
+                            for (int c = 0; c < C; ++c) {
+                                const int ncol = c * T + g * 4;
+                                const uint32_t off = rowoff + (uint32_t)(ncol >> 6) * G::SN +
+                                                     (((((uint32_t)ncol & 63) >> 3) << 4) ^ usw) + (uint32_t)(ncol & 4) * 2;
+                                uint2 hi, lo;
+                                split2(out[c][0], out[c][1], hi.x, lo.x);
+                                split2(out[c][2], out[c][3], hi.y, lo.y);
+                                *reinterpret_cast<uint2*>(sB + off) = hi;
+                                if constexpr (PASSES == 3) *reinterpret_cast<uint2*>(sB + G::B_PART + off) = lo;
+                                if (gp_l) {
+                                    // wgrad operand words (hi | lo << 16); forward tail points (>= n) must be exact zeros
+                                    uint32_t* dst = gp_l + c * plane_stride + goff;
+                                    uint32_t w0 = __byte_perm(hi.x, lo.x, 0x5410), w1 = __byte_perm(hi.x, lo.x, 0x7632);
+                                    uint32_t w2 = __byte_perm(hi.y, lo.y, 0x5410), w3 = __byte_perm(hi.y, lo.y, 0x7632);
+                                    if constexpr (FULL) {
+                                        dst[0] = w0; dst[H] = w1; dst[2 * H] = w2; dst[3 * H] = w3;
+                                    } else {
+                                        if (!BWD) {
+                                            if (pg + 0 >= a.n) w0 = 0;
+                                            if (pg + 1 >= a.n) w1 = 0;
+                                            if (pg + 2 >= a.n) w2 = 0;
+                                            if (pg + 3 >= a.n) w3 = 0;
+                                        }
+                                        if (pg + 0 < a.n_pad) dst[0] = w0;
+                                        if (pg + 1 < a.n_pad) dst[H] = w1;
+                                        if (pg + 2 < a.n_pad) dst[2 * H] = w2;
+                                        if (pg + 3 < a.n_pad) dst[3 * H] = w3;
+                                    }
                                 }
-                                if (pg + 0 < a.n_pad) dst[0] = w0;
-                                if (pg + 1 < a.n_pad) dst[H] = w1;
-                                if (pg + 2 < a.n_pad) dst[2 * H] = w2;
-                                if (pg + 3 < a.n_pad) dst[3 * H] = w3;
                             }
                         }
                     }
-                }
-                // ---------------- end of step -----------------------------------------------------------------------------
-                if (BWD) {
-                    if (j == 0) atomicAdd(a.dw_last + u, wlsum);
-                    if (l >= 1) {
-                        atomicAdd(a.db[l] + u, 30.f * bsum);
-                    } else {
-                        if (!a.sb_grad) atomicAdd(a.db[0] + u, 30.f * bsum);
-                        if constexpr (D > 0) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 0, 30.f * w0s0);
-                        if constexpr (D > 1) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 1, 30.f * w0s1);
-                        if constexpr (D > 2) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 2, 30.f * w0s2);
+                    // ---------------- end of step ---------------------------------------------------------------------------
+                    if (BWD) {
+                        if (j == 0) atomicAdd(a.dw_last + u, wlsum);
+                        if (l >= 1) {
+                            atomicAdd(a.db[l] + u, 30.f * bsum);
+                        } else {
+                            if (!a.sb_grad) atomicAdd(a.db[0] + u, 30.f * bsum);
+                            if constexpr (D > 0) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 0, 30.f * w0s0);
+                            if constexpr (D > 1) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 1, 30.f * w0s1);
+                            if constexpr (D > 2) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 2, 30.f * w0s2);
+                        }
+                    }
+                    if (!last) {
+                        fence_proxy_async();
+                        tc_fence_before();
+                        mbar_arrive(&b_ready[ctx]);
                     }
                 }
-                if (!last) {
-                    fence_proxy_async();
-                    tc_fence_before();
-                    mbar_arrive(b_ready);
-                }
-            }
+            };
+            if (full) run_tile(std::true_type{});
+            else run_tile(std::false_type{});
+
             if constexpr (!BWD) {
                 // ---- last layer: sum the per-unit-block partials, apply the output head ------------------------------
-                asm volatile("bar.sync 1, 512;" ::: "memory");
-                for (int e = tid; e < T; e += EPI_THREADS) {
+                named_bar_sync(1 + ctx, G::ETHREADS);
+                for (int e = etid; e < T; e += G::ETHREADS) {
                     int64_t gp = p0 + e;
                     if (gp < a.n) {
                         float v[C];
@@ -536,7 +564,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                     }
                 }
             }
-            asm volatile("bar.sync 1, 512;" ::: "memory");   // sXyz / sHead / sUbar are rewritten by the next tile
+            named_bar_sync(1 + ctx, G::ETHREADS);   // sXyz / sHead / sUbar are rewritten by the next tile
         }
     }
     tc_fence_before();
@@ -635,8 +663,9 @@ static int launch(const CUtensorMap& tmap, const Args& a, cudaStream_t st) {
         if (e != cudaSuccess) { set_error("tc net: smem attribute (%d B): %s", G::SMEM_BYTES, cudaGetErrorString(e)); return DIGS_ECUDA; }
         attr_set = true;
     }
-    int64_t tiles = (a.n + G::T - 1) / G::T;
-    int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    int64_t tiles = (a.n_pad + G::T - 1) / G::T;
+    int64_t rounds = (tiles + G::NCTX - 1) / G::NCTX;
+    int grid = (int)(rounds < num_sms() ? rounds : num_sms());
     kern<<<grid, NTHREADS, G::SMEM_BYTES, st>>>(tmap, a);
     count_launch();
     cudaError_t e = cudaGetLastError();
