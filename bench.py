@@ -157,6 +157,7 @@ def workload_config(args, world):
                         "4x256 sine MLP MFGI init, DiGSLoss siren_wo_n_w_div/l1",
             "points_per_step_per_gpu": 2 * N_POINTS, "hidden": H, "hidden_layers": LH, "in_dim": D,
             "precision_mode": args.mode, "parallelism": "dp%d (points sharded, 1 allreduce of 264449 fp32 grads)" % world,
+            "step_api": "eager autograd" if args.no_graph else "digs_b200.GraphedStep (CUDA graph replay)",
             "l2": "256 MiB scratch written between timed steps (L2 flush); per-step events exclude the flush"}
 
 
@@ -186,26 +187,38 @@ def run_ours(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     h2d_bytes = sum(t.numel() * 4 for t in hb[0])
 
+    graphed = None
+    if not args.no_graph:
+        # public API digs_b200.GraphedStep: zero-fill + both forward jets + DiGSLoss + reverse pass as ONE CUDA graph
+        graphed = digs_b200.GraphedStep(net, crit, N_POINTS, N_POINTS, batch=1, flat=flat)
+
     def step_resident(i):
         m, nrm, nm = db[i]
-        m = m.detach().requires_grad_()
-        nm = nm.detach().requires_grad_()
-        flat.zero_()
-        out = net(nm, m)
-        ld, _ = crit(out, m, nm, nrm)
-        ld["loss"].backward()
+        if graphed is not None:
+            ld = graphed.step(m, nm, nrm)
+        else:
+            m = m.detach().requires_grad_()
+            nm = nm.detach().requires_grad_()
+            flat.zero_()
+            out = net(nm, m)
+            ld, _ = crit(out, m, nm, nrm)
+            ld["loss"].backward()
         flat.extra[0] = ld["loss"].detach()
         flat.allreduce()
         return ld
 
     def step_e2e(i):
-        m, nrm, nm = (t.to(dev, non_blocking=True) for t in hb[i])
-        m.requires_grad_()
-        nm.requires_grad_()
-        flat.zero_()
-        out = net(nm, m)
-        ld, _ = crit(out, m, nm, nrm)
-        ld["loss"].backward()
+        if graphed is not None:
+            m, nrm, nm = hb[i]                      # pinned host tensors: GraphedStep.step copies them in asynchronously
+            ld = graphed.step(m, nm, nrm)
+        else:
+            m, nrm, nm = (t.to(dev, non_blocking=True) for t in hb[i])
+            m.requires_grad_()
+            nm.requires_grad_()
+            flat.zero_()
+            out = net(nm, m)
+            ld, _ = crit(out, m, nm, nrm)
+            ld["loss"].backward()
         flat.extra[0] = ld["loss"].detach()
         flat.allreduce()
         return float(flat.extra[0].item())        # D2H read of the step's result
@@ -234,6 +247,8 @@ def run_ours(args, rank, world, local_rank):
         evs.append((e0, e1))
     barrier()
     launches = (L.digs_launch_count() - launches0) / max(args.steps, 1)
+    if graphed is not None:
+        launches = graphed.launches_per_step      # library kernels recorded in (and replayed from) the graph each step
     ms_dev = sum(a.elapsed_time(b) for a, b in evs) / args.steps
 
     # ---- end-to-end timing (host buffers in, loss scalar out, every step) --------------------------
@@ -309,6 +324,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("DIGS_BENCH_MODE", "bf16x2"), choices=["fp32", "bf16x2", "bf16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="eager autograd step instead of digs_b200.GraphedStep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -8,6 +8,7 @@ All arithmetic runs in libdigs_b200.so (C-ABI in include/digs_b200.h); there is 
 from .network import DiGSNetwork, Decoder, FCBlock, Sine
 from .losses import DiGSLoss
 from .grid import implicit2mesh, get_3d_grid, grid_axes, grid_query, slab_range
+from .graph import GraphedStep
 
 __all__ = ["DiGSNetwork", "Decoder", "FCBlock", "Sine", "DiGSLoss", "implicit2mesh", "get_3d_grid", "grid_axes",
-           "grid_query", "slab_range"]
+           "grid_query", "slab_range", "GraphedStep"]

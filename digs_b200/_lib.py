@@ -39,7 +39,7 @@ class DigsGrads(ctypes.Structure):
 EXPORTS = (
     "digs_abi_version", "digs_last_error", "digs_launch_count", "digs_saved_bytes", "digs_forward_workspace_bytes",
     "digs_backward_workspace_bytes", "digs_value_workspace_bytes", "digs_grid_workspace_bytes",
-    "digs_jet_forward", "digs_jet_backward", "digs_loss_fused", "digs_value_forward", "digs_grid_query",
+    "digs_jet_forward", "digs_jet_backward", "digs_loss_fused", "digs_loss_fused_dw", "digs_value_forward", "digs_grid_query",
 )
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdigs_b200.so")
@@ -78,6 +78,9 @@ def lib():
     L.digs_loss_fused.restype = i32
     L.digs_loss_fused.argtypes = [vp, vp, i64, vp, vp, vp, i64, vp, i32, ctypes.POINTER(ctypes.c_float), i32, i32,
                                   i32, ctypes.c_float, i64, i64, vp, vp, vp, vp, vp, vp, vp]
+    L.digs_loss_fused_dw.restype = i32
+    L.digs_loss_fused_dw.argtypes = [vp, vp, i64, vp, vp, vp, i64, vp, i32, vp, i32, i32,
+                                     i32, ctypes.c_float, i64, i64, vp, vp, vp, vp, vp, vp, vp]
     L.digs_value_forward.restype = i32
     L.digs_value_forward.argtypes = [netp, vp, i64, i64, vp, i64, vp, vp, sz, i32, vp]
     L.digs_grid_query.restype = i32

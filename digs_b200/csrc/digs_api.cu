@@ -158,18 +158,38 @@ int digs_jet_backward(const DigsNet* net, const float* xyz, int64_t n, int64_t x
                               saved, workspace, grads, shape_bias ? shape_bias_grad : nullptr, (cudaStream_t)stream);
 }
 
-int digs_loss_fused(const float* f_m, const float* g_m, int64_t nm, const float* f_n, const float* g_n,
-                    const float* lap_n, int64_t nn, const float* normals, int d, const float* weights, int add_normal,
-                    int use_div, int div_l2, float div_clamp, int64_t Nm_total, int64_t Nn_total, float* fbar_m,
-                    float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n, float* terms_out, void* stream) {
-    if (!weights || !terms_out) { set_error("loss_fused: NULL weights/terms"); return DIGS_EINVAL; }
+static int loss_fused_checked(const float* f_m, const float* g_m, int64_t nm, const float* f_n, const float* g_n,
+                             const float* lap_n, int64_t nn, const float* normals, int d, const float* weights,
+                             const float* weights_device, int add_normal, int use_div, int div_l2, float div_clamp,
+                             int64_t Nm_total, int64_t Nn_total, float* fbar_m, float* gbar_m, float* fbar_n,
+                             float* gbar_n, float* lbar_n, float* terms_out, void* stream) {
+    if ((!weights && !weights_device) || !terms_out) { set_error("loss_fused: NULL weights/terms"); return DIGS_EINVAL; }
     if (nm < 0 || nn < 0) { set_error("loss_fused: negative count"); return DIGS_EINVAL; }
     if (nm > 0 && (!f_m || !g_m || !fbar_m || !gbar_m)) { set_error("loss_fused: NULL manifold buffer"); return DIGS_EINVAL; }
     if (nn > 0 && (!f_n || !g_n || !fbar_n || !gbar_n)) { set_error("loss_fused: NULL non-manifold buffer"); return DIGS_EINVAL; }
     if (use_div && nn > 0 && (!lap_n || !lbar_n)) { set_error("loss_fused: div loss without lap buffers"); return DIGS_EINVAL; }
     if (add_normal && !normals) { set_error("loss_fused: normal term without normals"); return DIGS_EINVAL; }
     return loss_fused(f_m, g_m, nm, f_n, g_n, lap_n, nn, normals, d, weights, add_normal, use_div, div_l2, div_clamp,
-                      Nm_total, Nn_total, fbar_m, gbar_m, fbar_n, gbar_n, lbar_n, terms_out, (cudaStream_t)stream);
+                      Nm_total, Nn_total, fbar_m, gbar_m, fbar_n, gbar_n, lbar_n, terms_out, weights_device,
+                      (cudaStream_t)stream);
+}
+
+int digs_loss_fused(const float* f_m, const float* g_m, int64_t nm, const float* f_n, const float* g_n,
+                    const float* lap_n, int64_t nn, const float* normals, int d, const float* weights, int add_normal,
+                    int use_div, int div_l2, float div_clamp, int64_t Nm_total, int64_t Nn_total, float* fbar_m,
+                    float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n, float* terms_out, void* stream) {
+    return loss_fused_checked(f_m, g_m, nm, f_n, g_n, lap_n, nn, normals, d, weights, nullptr, add_normal, use_div, div_l2,
+                              div_clamp, Nm_total, Nn_total, fbar_m, gbar_m, fbar_n, gbar_n, lbar_n, terms_out, stream);
+}
+
+int digs_loss_fused_dw(const float* f_m, const float* g_m, int64_t nm, const float* f_n, const float* g_n,
+                       const float* lap_n, int64_t nn, const float* normals, int d, const float* weights_device,
+                       int add_normal, int use_div, int div_l2, float div_clamp, int64_t Nm_total, int64_t Nn_total,
+                       float* fbar_m, float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n, float* terms_out,
+                       void* stream) {
+    return loss_fused_checked(f_m, g_m, nm, f_n, g_n, lap_n, nn, normals, d, nullptr, weights_device, add_normal, use_div,
+                              div_l2, div_clamp, Nm_total, Nn_total, fbar_m, gbar_m, fbar_n, gbar_n, lbar_n, terms_out,
+                              stream);
 }
 
 int digs_value_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_stride, const float* shape_bias,

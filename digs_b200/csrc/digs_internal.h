@@ -91,6 +91,6 @@ int loss_fused(const float* f_m, const float* g_m, int64_t nm, const float* f_n,
                const float* lap_n, int64_t nn, const float* normals, int d, const float* weights,
                int add_normal, int use_div, int div_l2, float div_clamp, int64_t Nm_total, int64_t Nn_total,
                float* fbar_m, float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n, float* terms_out,
-               cudaStream_t st);
+               const float* weights_device, cudaStream_t st);
 
 }  // namespace digs

@@ -14,6 +14,7 @@ struct LossArgs {
     float *fbar_m, *gbar_m, *fbar_n, *gbar_n, *lbar_n, *terms;
     int64_t nm, nn;
     float w_sdf, w_inter, w_normal, w_eik, w_div;
+    const float* w_dev;   // optional DEVICE copy of the weights (CUDA-graph replays re-read it every launch)
     float inv_nm, inv_nn, inv_nall;
     float div_clamp;
     int add_normal, use_div, div_l2;
@@ -23,6 +24,9 @@ __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 
 
 template <int D>
 __global__ void __launch_bounds__(256) k_loss(LossArgs a) {
+    if (a.w_dev) {
+        a.w_sdf = a.w_dev[0]; a.w_inter = a.w_dev[1]; a.w_normal = a.w_dev[2]; a.w_eik = a.w_dev[3]; a.w_div = a.w_dev[4];
+    }
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float t_sdf = 0.f, t_inter = 0.f, t_eik = 0.f, t_nrm = 0.f, t_div = 0.f;
     if (i < a.nm) {
@@ -107,15 +111,19 @@ __global__ void __launch_bounds__(256) k_loss(LossArgs a) {
             case 3: wt = a.add_normal ? a.w_normal : 0.f; break;
             default: wt = a.use_div ? a.w_div : 0.f; break;
         }
-        if (wt != 0.f) atomicAdd(a.terms, wt * t);
+        atomicAdd(a.terms, wt * t);
     }
 }
 
 int loss_fused(const float* f_m, const float* g_m, int64_t nm, const float* f_n, const float* g_n,
                const float* lap_n, int64_t nn, const float* normals, int d, const float* weights, int add_normal,
                int use_div, int div_l2, float div_clamp, int64_t Nm_total, int64_t Nn_total, float* fbar_m,
-               float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n, float* terms_out, cudaStream_t st) {
+               float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n, float* terms_out,
+               const float* weights_device, cudaStream_t st) {
     LossArgs a;
+    a.w_dev = weights_device;
+    static const float zero_w[6] = {0, 0, 0, 0, 0, 0};
+    if (!weights) weights = zero_w;
     a.f_m = f_m; a.g_m = g_m; a.f_n = f_n; a.g_n = g_n; a.lap_n = lap_n; a.normals = normals;
     a.fbar_m = fbar_m; a.gbar_m = gbar_m; a.fbar_n = fbar_n; a.gbar_n = gbar_n; a.lbar_n = lbar_n;
     a.terms = terms_out;

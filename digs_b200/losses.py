@@ -40,10 +40,17 @@ class _FusedLoss(torch.autograd.Function):
         terms = torch.zeros(8, dtype=torch.float32, device=dev)
         w = (ctypes.c_float * 6)(*[float(x) for x in (list(cfg["weights"]) + [0.0] * 6)[:6]])
         Nm_tot, Nn_tot = cfg["global_counts"] if cfg["global_counts"] is not None else (nm, nn_)
-        rc = L.digs_loss_fused(_ptr(f_m), _ptr(g_m), nm, _ptr(f_n), _ptr(g_n), _ptr(lap), nn_, _ptr(nrm), d, w,
-                               int(cfg["add_normal"]), int(cfg["use_div"]), int(cfg["div_l2"]),
-                               float(cfg["div_clamp"]), int(Nm_tot), int(Nn_tot),
-                               _ptr(fb_m), _ptr(gb_m), _ptr(fb_n), _ptr(gb_n), _ptr(lb_n), _ptr(terms), _stream())
+        wdev = cfg.get("device_weights")
+        if wdev is not None:      # CUDA-graph mode: weights live on the device and are re-read at every replay
+            rc = L.digs_loss_fused_dw(_ptr(f_m), _ptr(g_m), nm, _ptr(f_n), _ptr(g_n), _ptr(lap), nn_, _ptr(nrm), d,
+                                      _ptr(wdev), int(cfg["add_normal"]), int(cfg["use_div"]), int(cfg["div_l2"]),
+                                      float(cfg["div_clamp"]), int(Nm_tot), int(Nn_tot),
+                                      _ptr(fb_m), _ptr(gb_m), _ptr(fb_n), _ptr(gb_n), _ptr(lb_n), _ptr(terms), _stream())
+        else:
+            rc = L.digs_loss_fused(_ptr(f_m), _ptr(g_m), nm, _ptr(f_n), _ptr(g_n), _ptr(lap), nn_, _ptr(nrm), d, w,
+                                   int(cfg["add_normal"]), int(cfg["use_div"]), int(cfg["div_l2"]),
+                                   float(cfg["div_clamp"]), int(Nm_tot), int(Nn_tot),
+                                   _ptr(fb_m), _ptr(gb_m), _ptr(fb_n), _ptr(gb_n), _ptr(lb_n), _ptr(terms), _stream())
         _lib.check(rc, "loss_fused")
         ctx.save_for_backward(fb_m, gb_m, fb_n, gb_n, *([lb_n] if lb_n is not None else []))
         ctx.has_lap = lb_n is not None
@@ -103,15 +110,16 @@ class DiGSLoss(nn.Module):
         if self.loss_type == "siren_wo_n":
             self.weights[2] = 0                                      # models/losses.py:153
         cfg = dict(weights=self.weights, add_normal=self.loss_type in _ADDS_NORMAL, use_div=self.use_div,
-                   div_l2=self.div_type == "l2", div_clamp=self.div_clamp, global_counts=self.global_counts)
+                   div_l2=self.div_type == "l2", div_clamp=self.div_clamp, global_counts=self.global_counts,
+                   device_weights=getattr(self, "device_weights", None))
         terms = _FusedLoss.apply(f_m, g_m, f_n, g_n, lap_n if self.use_div else None, mnfld_n_gt, cfg)
         loss = terms[0]
         det = terms.detach()
-        div_loss = det[5] if self.use_div else torch.tensor([0.0], device=device)
+        div_loss = det[5] if self.use_div else torch.zeros(1, device=device)
         if latent_reg is not None:
             latent_reg_term = latent_reg.mean()                       # models/losses.py:31-38
         else:
-            latent_reg_term = torch.tensor([0.0], device=device)
+            latent_reg_term = torch.zeros(1, device=device)
         if latent is not None and latent_reg is not None:
             loss = loss + self.weights[5] * latent_reg_term          # models/losses.py:183-184
         curv = torch.zeros((), device=device)

@@ -125,6 +125,15 @@ int digs_loss_fused(const float* f_m, const float* g_m, int64_t nm, const float*
                     float* fbar_m, float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n,
                     float* terms_out, void* stream);
 
+/* Same, with the six weights read from DEVICE memory at kernel time: for CUDA-graph replays, where the div weight
+ * that update_div_weight (models/losses.py:190-228) rewrites every iteration must not be baked into the graph. */
+int digs_loss_fused_dw(const float* f_m, const float* g_m, int64_t nm, const float* f_n, const float* g_n,
+                       const float* lap_n, int64_t nn, const float* normals, int d,
+                       const float* weights_device, int add_normal, int use_div, int div_l2, float div_clamp,
+                       int64_t Nm_total, int64_t Nn_total,
+                       float* fbar_m, float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n,
+                       float* terms_out, void* stream);
+
 /* decoder(points) -> (n) values, no derivative channels, nothing saved. */
 int digs_value_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_stride,
                        const float* shape_bias, int64_t pts_per_shape, float* f,

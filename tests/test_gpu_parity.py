@@ -343,3 +343,29 @@ def test_in_place_gradient_accumulation_matches_autograd(precision):
             assert flat.flat[:-8].abs().sum() > 0
     for a, b in zip(*grads):
         assert maxrel(b.cpu(), a.cpu()) < 1e-5
+
+
+def test_graphed_step_matches_eager_and_follows_weight_updates():
+    """digs_b200.GraphedStep (CUDA-graph replay) = the eager step, including a div-weight change between replays."""
+    case = STEP_CASES["c2_small"]
+    g = golden("step_c2_small.npz")
+    m = torch.tensor(g["in_mnfld"], device=DEV)
+    nm = torch.tensor(g["in_nonmnfld"], device=DEV)
+    nrm = torch.tensor(g["in_normals"], device=DEV)
+    net_g = build_net(case["net"], case["seed"], precision="bf16x2").to(DEV)
+    crit_g = digs_b200.DiGSLoss(**copy.deepcopy(case["loss"]))
+    gs = digs_b200.GraphedStep(net_g, crit_g, m.shape[1], nm.shape[1], batch=m.shape[0])
+    assert gs.launches_per_step > 0
+    for w_div in (1e2, 37.0, 0.0):
+        crit_g.weights[4] = w_div
+        ld_g = gs.step(m, nm, nrm)
+        grads_g = [p.grad.detach().clone() for p in net_g.parameters()]
+        net_e = build_net(case["net"], case["seed"], precision="bf16x2").to(DEV)
+        crit_e = digs_b200.DiGSLoss(**copy.deepcopy(case["loss"]))
+        crit_e.weights[4] = w_div
+        me, nme = m.clone().requires_grad_(), nm.clone().requires_grad_()
+        ld_e, _ = crit_e(net_e(nme, me), me, nme, nrm)
+        ld_e["loss"].backward()
+        assert abs(float(ld_g["loss"]) - float(ld_e["loss"])) <= 1e-5 * abs(float(ld_e["loss"]))
+        for a, b in zip(grads_g, [p.grad for p in net_e.parameters()]):
+            assert maxrel(a.cpu(), b.cpu()) < 1e-4
