@@ -187,3 +187,78 @@ class JetFunction(torch.autograd.Function):
             if fb is not None:
                 xyz_grad[:, :ctx.spec.d] = fb[:, None] * g
         return (xyz_grad, sb_grad, None, None, None, None, *grads)
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+class JetPairFunction(torch.autograd.Function):
+    """Jets of the off-surface cloud (with Laplacian) and the surface cloud (without) as ONE autograd node.
+
+    The two clouds are independent, so their kernels are issued on two streams and joined before returning: the persistent
+    kernels of one cloud fill the SMs that the other cloud's last, partially filled wave of tiles leaves idle.  Keeping the
+    fork / join inside a single node means autograd (and CUDA-graph capture) only ever sees the caller's stream.
+    Parameter gradients of both clouds are summed (or accumulated in place, see JetFunction)."""
+
+    @staticmethod
+    def forward(ctx, xyz_n, xyz_m, sb_n, sb_m, spec, pps_n, pps_m, lap_n, mode, *params):
+        ctx.grad_targets = None
+        if getattr(spec, "accumulate_in_place", False) and all(
+                p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 for p in params):
+            ctx.grad_targets = [p.grad for p in params]
+        params = [p.detach() for p in params]
+        xn, xm = xyz_n.detach(), xyz_m.detach()
+        sbn = None if sb_n is None else sb_n.detach().contiguous()
+        sbm = None if sb_m is None else sb_m.detach().contiguous()
+        main = torch.cuda.current_stream(xn.device)
+        side = _side_stream(xn.device)
+        side.wait_stream(main)
+        fn, gn, ln, saved_n = jet_forward_raw(spec, params, xn, sbn, pps_n, lap_n, True, mode)
+        with torch.cuda.stream(side):
+            fm, gm, _, saved_m = jet_forward_raw(spec, params, xm, sbm, pps_m, False, True, mode)
+        main.wait_stream(side)
+        ctx.spec, ctx.pps_n, ctx.pps_m, ctx.lap_n, ctx.mode = spec, pps_n, pps_m, lap_n, mode
+        ctx.has_sb = sbn is not None
+        ctx.save_for_backward(xn, xm, saved_n, saved_m, *([sbn, sbm] if sbn is not None else []), *params)
+        ctx.set_materialize_grads(False)
+        if ln is None:
+            ln = torch.empty(0, dtype=torch.float32, device=xn.device)
+            ctx.mark_non_differentiable(ln)
+        return fn, gn, ln, fm, gm
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, fn_bar, gn_bar, ln_bar, fm_bar, gm_bar):
+        t = ctx.saved_tensors
+        xn, xm, saved_n, saved_m = t[0], t[1], t[2], t[3]
+        k = 4
+        sbn = sbm = None
+        if ctx.has_sb:
+            sbn, sbm = t[4], t[5]
+            k = 6
+        params = list(t[k:])
+        c = lambda v: None if v is None else v.contiguous()
+        if not ctx.lap_n:
+            ln_bar = None
+        direct = ctx.grad_targets
+        main = torch.cuda.current_stream(xn.device)
+        side = _side_stream(xn.device)
+        side.wait_stream(main)
+        gr_n, sbg_n = jet_backward_raw(ctx.spec, params, xn, sbn, ctx.pps_n, ctx.lap_n, c(fn_bar), c(gn_bar), c(ln_bar),
+                                       saved_n, ctx.mode, grad_out=direct)
+        with torch.cuda.stream(side):
+            gr_m, sbg_m = jet_backward_raw(ctx.spec, params, xm, sbm, ctx.pps_m, False, c(fm_bar), c(gm_bar), None,
+                                           saved_m, ctx.mode, grad_out=direct)
+        main.wait_stream(side)
+        if direct is not None:
+            grads = [None] * len(params)
+        else:
+            grads = [a + b for a, b in zip(gr_n, gr_m)]
+        return (None, None, sbg_n, sbg_m, None, None, None, None, None, *grads)

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .jet import JetFunction, NetSpec, value_forward_raw
+from .jet import JetFunction, JetPairFunction, NetSpec, value_forward_raw
 
 OMEGA = 30.0
 _MFGI_PERIODS = (1, 30)           # models/DiGS.py:218
@@ -262,12 +262,28 @@ class DiGSNetwork(nn.Module):
     def forward(self, non_mnfld_pnts, mnfld_pnts=None):
         latent = latent_reg = None
         m_pred = m_grad = None
-        if mnfld_pnts is not None:
-            if self.encoder_type == "autodecoder":
-                latent = non_mnfld_pnts[:, :, 3:]                      # models/DiGS.py:48
-                latent_reg = latent.norm(dim=-1).mean()
-            m_pred, m_grad, _ = self._cloud(mnfld_pnts, want_lap=False)
-        n_pred, n_grad, n_lap = self._cloud(non_mnfld_pnts, want_lap=self.compute_laplacian)
+        if mnfld_pnts is not None and self.encoder_type == "autodecoder":
+            latent = non_mnfld_pnts[:, :, 3:]                          # models/DiGS.py:48
+            latent_reg = latent.norm(dim=-1).mean()
+        paired = (mnfld_pnts is not None and torch.is_grad_enabled() and mnfld_pnts.requires_grad
+                  and non_mnfld_pnts.requires_grad and mnfld_pnts.is_cuda and non_mnfld_pnts.is_cuda)
+        if paired:
+            # both clouds as one autograd node, their kernels overlapped on two streams (JetPairFunction)
+            fc = self.decoder.fc_block
+            bs, n_n, n_m = non_mnfld_pnts.shape[0], non_mnfld_pnts.shape[1], mnfld_pnts.shape[1]
+            flat_n = non_mnfld_pnts.reshape(-1, non_mnfld_pnts.shape[-1]).float().contiguous()
+            flat_m = mnfld_pnts.reshape(-1, mnfld_pnts.shape[-1]).float().contiguous()
+            sb_n, pps_n = fc._split_latent(flat_n, n_n)
+            sb_m, pps_m = fc._split_latent(flat_m, n_m)
+            fn, gn, ln, fm, gm = JetPairFunction.apply(flat_n.detach(), flat_m.detach(), sb_n, sb_m, fc.spec(), pps_n, pps_m,
+                                                       bool(self.compute_laplacian), fc.mode(), *fc.flat_params())
+            n_pred, n_grad = fn.reshape(bs, n_n), gn.reshape(bs, n_n, self.in_dim)
+            n_lap = ln.reshape(bs, n_n) if self.compute_laplacian else None
+            m_pred, m_grad = fm.reshape(bs, n_m), gm.reshape(bs, n_m, self.in_dim)
+        else:
+            if mnfld_pnts is not None:
+                m_pred, m_grad, _ = self._cloud(mnfld_pnts, want_lap=False)
+            n_pred, n_grad, n_lap = self._cloud(non_mnfld_pnts, want_lap=self.compute_laplacian)
         return {"manifold_pnts_pred": m_pred,
                 "nonmanifold_pnts_pred": n_pred,
                 "latent_reg": latent_reg,
