@@ -280,10 +280,28 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     ms_fwd = sum(a.elapsed_time(b) for a, b in kev) / reps
 
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    # ---- second half of the metric: MC grid queries/s, grid_res^3 points sharded by iy slab over the ranks -----
+    ms_grid, grid_pts = 0.0, 0
+    if args.grid_res > 0:
+        axes, _, _ = digs_b200.grid_axes(args.grid_res, np.array([[-1, 1], [-1, 1], [-1, 1]], dtype=float))
+        ny = len(axes[1])
+        slab = digs_b200.slab_range(ny, rank, world)
+        out_vol = torch.empty((slab[1] - slab[0], len(axes[0]), len(axes[2])), dtype=torch.float32, device=dev)
+        small = digs_b200.slab_range(ny, 0, 16 * world)
+        digs_b200.grid_query(net, axes, iy_range=small)                      # warm-up
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        digs_b200.grid_query(net, axes, iy_range=slab, out=out_vol)
+        e1.record()
+        barrier()
+        ms_grid = e0.elapsed_time(e1)
+        grid_pts = len(axes[0]) * ny * len(axes[2])
+
+    t = torch.tensor([ms_dev, ms_e2e, ms_grid], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    ms_dev, ms_e2e, ms_grid = float(t[0]), float(t[1]), float(t[2])
     if rank == 0:
         peaks = measured_peaks()
         pts = 2 * N_POINTS * world
@@ -307,6 +325,14 @@ def run_ours(args, rank, world, local_rank):
                                             "frac": step_tflops / peaks["sustained"],
                                             "algorithmic_gflop": FLOP_STEP / 1e9,
                                             "peak_source": peaks["source"] + " bf16 dense sustained"}}}
+        if args.grid_res > 0:
+            flop_pt = 2 * LH * H * H + 2 * D * H + 2 * H
+            gt = grid_pts * flop_pt / (ms_grid * 1e-3) / 1e12
+            line["grid_query"] = {"metric": "MC grid queries/sec", "value": grid_pts / (ms_grid * 1e-3), "unit": "queries/s",
+                                  "grid": "%d^3, bbox [-1,1]^3 + 0.1, fp16-rounded axes, iy slabs over %d rank(s)" % (args.grid_res, world),
+                                  "ms": ms_grid, "output": "fp32 volume resident in HBM",
+                                  "roofline": {"bound": "tensor", "achieved": gt, "peak": peaks["sustained"], "unit": "TFLOP/s",
+                                               "frac": gt / peaks["sustained"], "algorithmic_mflop_per_query": flop_pt / 1e6}}
         if world == 1 and not args.no_cpu:
             v, ms, cores, sample = cpu_reference_steps(3, 1)
             line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample,
@@ -324,6 +350,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("DIGS_BENCH_MODE", "bf16x2"), choices=["fp32", "bf16x2", "bf16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--grid-res", type=int, default=512, help="resolution of the grid-query leg (0 disables it)")
     ap.add_argument("--no-graph", action="store_true", help="eager autograd step instead of digs_b200.GraphedStep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
