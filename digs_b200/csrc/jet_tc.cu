@@ -56,8 +56,9 @@ struct Cfg {
     // the operand fetch (not the tensor pipe) becomes the limit.  The code keeps the context machinery; NCTX stays 1.
     static constexpr int NCTX = 1;
     static constexpr int N = (H_ > 256) ? 64 : 128;   // UMMA N = operand columns per context (64 keeps X in smem at H=512)
-    static constexpr int T = (N / C) / 4 * 4;         // points per tile (whole 4-point groups)
-    static constexpr int NGRP = T / 4;
+    static constexpr int GP = (C == 1) ? 8 : 4;       // points per epilogue group (one tcgen05.ld per channel)
+    static constexpr int T = (N / C) / GP * GP;       // points per tile (whole groups)
+    static constexpr int NGRP = T / GP;
     static constexpr int MT = H / 128;                // UMMA M tiles
     static constexpr int NG = N / 64;                 // 64-column groups of the MN-major operand
     static constexpr int SN = 1024;                   // byte stride between column groups   (descriptor LBO)
@@ -166,7 +167,8 @@ template <int D, int LAP, int H, int PASSES, bool BWD>
 __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ CUtensorMap tmapW, Args a) {
     using G = Cfg<D, LAP, H, PASSES>;
     constexpr int C = G::C, T = G::T, N = G::N, MT = G::MT, NCTX = G::NCTX;
-    constexpr int P2 = (C * 4 <= 4) ? 4 : ((C * 4 <= 16) ? 16 : 32);   // padded size of the head partial-sum vector
+    constexpr int GP = G::GP;
+    constexpr int P2 = (C * GP <= 4) ? 4 : ((C * GP <= 16) ? 16 : 32);   // padded size of the head partial-sum vector
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sRing = smem + G::OFF_RING;
@@ -313,11 +315,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
             }
             named_bar_sync(1 + ctx, G::ETHREADS);
             // per-tile base pointers of this thread's unit column (point p0 + 4*gpart, channel 0, layer slot 0)
-            float* pl_tile = a.planes_t ? a.planes_t + (p0 + gpart * 4) * H + u : nullptr;
+            float* pl_tile = a.planes_t ? a.planes_t + (p0 + gpart * GP) * H + u : nullptr;
             uint32_t* gp_tile = nullptr;
             {
                 __nv_bfloat16* gq = BWD ? a.GT : a.actT;
-                if (gq) gp_tile = reinterpret_cast<uint32_t*>(gq) + (p0 + gpart * 4) * H + u;
+                if (gq) gp_tile = reinterpret_cast<uint32_t*>(gq) + (p0 + gpart * GP) * H + u;
             }
 
             auto run_tile = [&](auto full_tag) {
@@ -341,19 +343,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                     for (int gi = 0; gi < G::GITER; ++gi) {
                         const int g = gpart + gi * G::GS;
                         if (G::GS > 1 && g >= G::NGRP) break;
-                        const int64_t pg = p0 + g * 4;               // first point of the group
-                        const int goff = gi * G::GS * 4 * H;         // element offset of this group from the tile base pointers
-                        float acc[C][4];                              // TMEM values: fwd pre-activations, bwd incoming adjoint
+                        const int64_t pg = p0 + g * GP;              // first point of the group
+                        const int goff = gi * G::GS * GP * H;        // element offset of this group from the tile base pointers
+                        float acc[C][GP];                             // TMEM values: fwd pre-activations, bwd incoming adjoint
                         if (j > 0) {
 #pragma unroll
-                            for (int c = 0; c < C; ++c) tmem_ld4(t_base + c * T + g * 4, acc[c]);
+                            for (int c = 0; c < C; ++c) {
+                                if constexpr (GP == 8) tmem_ld8(t_base + c * T + g * GP, acc[c]);
+                                else tmem_ld4(t_base + c * T + g * GP, acc[c]);
+                            }
                             tmem_ld_wait();
                         }
-                        float pre[C][4];                              // scaled pre-activations (30 z | 30 Z_k | 30 Q) of layer l
+                        float pre[C][GP];                             // scaled pre-activations (30 z | 30 Z_k | 30 Q) of layer l
                         if ((!BWD && j == 0) || (BWD && l == 0)) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float* xp = sXyz + (g * 4 + i) * 3;
+                            for (int i = 0; i < GP; ++i) {
+                                const float* xp = sXyz + (g * GP + i) * 3;
                                 float bz = w0v.w;
                                 if (a.src.shape_bias) {
                                     int64_t gp = pg + i < a.n ? pg + i : a.n - 1;
@@ -371,13 +376,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
 #pragma unroll
                             for (int c = 0; c < C; ++c)
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) pre[c][i] = acc[c][i] + (c == 0 ? blv : 0.f);
+                                for (int i = 0; i < GP; ++i) pre[c][i] = acc[c][i] + (c == 0 ? blv : 0.f);
                             if (pl_l) {
 #pragma unroll
                                 for (int c = 0; c < C; ++c) {
                                     float* dst = pl_l + c * plane_stride + goff;
 #pragma unroll
-                                    for (int i = 0; i < 4; ++i)
+                                    for (int i = 0; i < GP; ++i)
                                         if (FULL || pg + i < a.n_pad) dst[i * H] = pre[c][i];
                                 }
                             }
@@ -386,7 +391,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                             for (int c = 0; c < C; ++c) {
                                 const float* srcp = pl_l + c * plane_stride + goff;
 #pragma unroll
-                                for (int i = 0; i < 4; ++i)
+                                for (int i = 0; i < GP; ++i)
                                     pre[c][i] = (FULL || pg + i < a.n_pad) ? __ldg(srcp + i * H) : 0.f;
                             }
                         }
@@ -394,12 +399,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
 #pragma unroll
                             for (int c = 0; c < C; ++c)
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) acc[c][i] = sUbar[(g * 4 + i) * C + c] * wl_u;
+                                for (int i = 0; i < GP; ++i) acc[c][i] = sUbar[(g * GP + i) * C + c] * wl_u;
                         }
                         // ---------------- per-point jet math ------------------------------------------------------------
-                        float out[C][4];   // fwd: layer outputs (h | A_k | P); bwd: scaled adjoints (zhat | Zhat_k | Qhat)
+                        float out[C][GP];  // fwd: layer outputs (h | A_k | P); bwd: scaled adjoints (zhat | Zhat_k | Qhat)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
+                        for (int i = 0; i < GP; ++i) {
                             float s, c;
                             sincos_reduced(pre[0][i], s, c);
                             float S2 = 0.f;
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                                 for (int k = 0; k < D; ++k) ZA = fmaf(pre[1 + k][i], acc[1 + k][i], ZA);
                                 if (j == 0) {
                                     // dL/dw_last: ubar . (h | A_k | P) of the last sine layer
-                                    const float* ubp = sUbar + (g * 4 + i) * C;
+                                    const float* ubp = sUbar + (g * GP + i) * C;
                                     float t = ubp[0] * s;
 #pragma unroll
                                     for (int k = 0; k < D; ++k) t = fmaf(ubp[1 + k], c * pre[1 + k][i], t);
@@ -441,8 +446,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                         if (BWD && l == 0) {
                             // layer-0 parameter gradients: dW0[u][k] += 30 (zhat x_k + Zhat_k), db0[u] += 30 zhat
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float* xp = sXyz + (g * 4 + i) * 3;
+                            for (int i = 0; i < GP; ++i) {
+                                const float* xp = sXyz + (g * GP + i) * 3;
                                 bsum += out[0][i];
                                 if constexpr (D > 0) w0s0 += fmaf(out[0][i], xp[0], out[1][i]);
                                 if constexpr (D > 1) w0s1 += fmaf(out[0][i], xp[1], out[2][i]);
@@ -453,42 +458,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                         } else if (!BWD && last) {
                             float part[P2];
 #pragma unroll
-                            for (int v = 0; v < P2; ++v) part[v] = (v < C * 4) ? out[v >> 2][v & 3] * wl_u : 0.f;
+                            for (int v = 0; v < P2; ++v) part[v] = (v < C * GP) ? out[v / GP][v % GP] * wl_u : 0.f;
                             warp_reduce_scatter<P2>(part, lane);
-                            if (lane < C * 4) sHead[ub * N + (lane >> 2) * T + g * 4 + (lane & 3)] = part[0];
+                            if (lane < C * GP) sHead[ub * N + (lane / GP) * T + g * GP + (lane % GP)] = part[0];
                         } else {
                             if (BWD) {
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) bsum += out[0][i];
+                                for (int i = 0; i < GP; ++i) bsum += out[0][i];
                             }
 #pragma unroll
                             for (int c = 0; c < C; ++c) {
-                                const int ncol = c * T + g * 4;
+                                const int ncol = c * T + g * GP;
                                 const uint32_t off = rowoff + (uint32_t)(ncol >> 6) * G::SN +
-                                                     (((((uint32_t)ncol & 63) >> 3) << 4) ^ usw) + (uint32_t)(ncol & 4) * 2;
-                                uint2 hi, lo;
-                                split2(out[c][0], out[c][1], hi.x, lo.x);
-                                split2(out[c][2], out[c][3], hi.y, lo.y);
-                                *reinterpret_cast<uint2*>(sB + off) = hi;
-                                if constexpr (PASSES == 3) *reinterpret_cast<uint2*>(sB + G::B_PART + off) = lo;
+                                                     (((((uint32_t)ncol & 63) >> 3) << 4) ^ usw) + (uint32_t)(ncol & (8 - GP)) * 2;
+                                uint32_t hi[GP / 2], lo[GP / 2];
+#pragma unroll
+                                for (int i = 0; i < GP / 2; ++i) split2(out[c][2 * i], out[c][2 * i + 1], hi[i], lo[i]);
+                                if constexpr (GP == 8) {
+                                    *reinterpret_cast<uint4*>(sB + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                                    if constexpr (PASSES == 3)
+                                        *reinterpret_cast<uint4*>(sB + G::B_PART + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                                } else {
+                                    *reinterpret_cast<uint2*>(sB + off) = make_uint2(hi[0], hi[1]);
+                                    if constexpr (PASSES == 3) *reinterpret_cast<uint2*>(sB + G::B_PART + off) = make_uint2(lo[0], lo[1]);
+                                }
                                 if (gp_l) {
                                     // wgrad operand words (hi | lo << 16); forward tail points (>= n) must be exact zeros
                                     uint32_t* dst = gp_l + c * plane_stride + goff;
-                                    uint32_t w0 = __byte_perm(hi.x, lo.x, 0x5410), w1 = __byte_perm(hi.x, lo.x, 0x7632);
-                                    uint32_t w2 = __byte_perm(hi.y, lo.y, 0x5410), w3 = __byte_perm(hi.y, lo.y, 0x7632);
-                                    if constexpr (FULL) {
-                                        dst[0] = w0; dst[H] = w1; dst[2 * H] = w2; dst[3 * H] = w3;
-                                    } else {
-                                        if (!BWD) {
-                                            if (pg + 0 >= a.n) w0 = 0;
-                                            if (pg + 1 >= a.n) w1 = 0;
-                                            if (pg + 2 >= a.n) w2 = 0;
-                                            if (pg + 3 >= a.n) w3 = 0;
+#pragma unroll
+                                    for (int i = 0; i < GP; ++i) {
+                                        uint32_t w = __byte_perm(hi[i >> 1], lo[i >> 1], (i & 1) ? 0x7632 : 0x5410);
+                                        if constexpr (FULL) {
+                                            dst[i * H] = w;
+                                        } else {
+                                            if (!BWD && pg + i >= a.n) w = 0;
+                                            if (pg + i < a.n_pad) dst[i * H] = w;
                                         }
-                                        if (pg + 0 < a.n_pad) dst[0] = w0;
-                                        if (pg + 1 < a.n_pad) dst[H] = w1;
-                                        if (pg + 2 < a.n_pad) dst[2 * H] = w2;
-                                        if (pg + 3 < a.n_pad) dst[3 * H] = w3;
                                     }
                                 }
                             }
