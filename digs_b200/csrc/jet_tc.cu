@@ -56,7 +56,7 @@ struct Cfg {
     // the operand fetch (not the tensor pipe) becomes the limit.  The code keeps the context machinery; NCTX stays 1.
     static constexpr int NCTX = 1;
     static constexpr int N = (H_ > 256) ? 64 : 128;   // UMMA N = operand columns per context (64 keeps X in smem at H=512)
-    static constexpr int GP = (C == 1) ? 8 : 4;       // points per epilogue group (one tcgen05.ld per channel)
+    static constexpr int GP = (C == 1) ? 16 : 4;      // points per epilogue group (one tcgen05.ld per channel)
     static constexpr int T = (N / C) / GP * GP;       // points per tile (whole groups)
     static constexpr int NGRP = T / GP;
     static constexpr int MT = H / 128;                // UMMA M tiles
@@ -349,7 +349,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                         if (j > 0) {
 #pragma unroll
                             for (int c = 0; c < C; ++c) {
-                                if constexpr (GP == 8) tmem_ld8(t_base + c * T + g * GP, acc[c]);
+                                if constexpr (GP == 16) tmem_ld16(t_base + c * T + g * GP, acc[c]);
+                                else if constexpr (GP == 8) tmem_ld8(t_base + c * T + g * GP, acc[c]);
                                 else tmem_ld4(t_base + c * T + g * GP, acc[c]);
                             }
                             tmem_ld_wait();
@@ -469,16 +470,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
 #pragma unroll
                             for (int c = 0; c < C; ++c) {
                                 const int ncol = c * T + g * GP;
-                                const uint32_t off = rowoff + (uint32_t)(ncol >> 6) * G::SN +
-                                                     (((((uint32_t)ncol & 63) >> 3) << 4) ^ usw) + (uint32_t)(ncol & (8 - GP)) * 2;
                                 uint32_t hi[GP / 2], lo[GP / 2];
 #pragma unroll
                                 for (int i = 0; i < GP / 2; ++i) split2(out[c][2 * i], out[c][2 * i + 1], hi[i], lo[i]);
-                                if constexpr (GP == 8) {
-                                    *reinterpret_cast<uint4*>(sB + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                                    if constexpr (PASSES == 3)
-                                        *reinterpret_cast<uint4*>(sB + G::B_PART + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                                if constexpr (GP >= 8) {
+#pragma unroll
+                                    for (int h = 0; h < GP / 8; ++h) {       // one 16-byte chunk per 8 points
+                                        const int nc = ncol + 8 * h;
+                                        const uint32_t off = rowoff + (uint32_t)(nc >> 6) * G::SN + (((((uint32_t)nc & 63) >> 3) << 4) ^ usw);
+                                        *reinterpret_cast<uint4*>(sB + off) = make_uint4(hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
+                                        if constexpr (PASSES == 3)
+                                            *reinterpret_cast<uint4*>(sB + G::B_PART + off) =
+                                                make_uint4(lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
+                                    }
                                 } else {
+                                    const uint32_t off = rowoff + (uint32_t)(ncol >> 6) * G::SN +
+                                                         (((((uint32_t)ncol & 63) >> 3) << 4) ^ usw) + (uint32_t)(ncol & 4) * 2;
                                     *reinterpret_cast<uint2*>(sB + off) = make_uint2(hi[0], hi[1]);
                                     if constexpr (PASSES == 3) *reinterpret_cast<uint2*>(sB + G::B_PART + off) = make_uint2(lo[0], lo[1]);
                                 }
