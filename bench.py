@@ -36,6 +36,10 @@ H, LH, D = 256, 4, 3
 FLOP_FWD_NONMNFLD = (2 + D) * 2 * LH * H * H
 FLOP_FWD_MNFLD = (1 + D) * 2 * LH * H * H
 FLOP_STEP = 3 * N_POINTS * (FLOP_FWD_NONMNFLD + FLOP_FWD_MNFLD)
+# dram__bytes_read.sum + dram__bytes_write.sum of the forward-jet kernel (C=5, 15000 points, saving for the reverse pass),
+# per launch, from the `ncu --set full` capture summarised in profiles/r01_full_tc_kernels.md.  The kernel's algorithmic
+# bytes are the saved planes + wgrad operand: 2 * 15000 * 4 layers * 5 channels * 256 units * 4 B = 614 MB.
+FWD_DRAM_BYTES = {"bf16x2": 559.65e6}
 
 
 def measured_peaks():
@@ -317,7 +321,7 @@ def run_ours(args, rank, world, local_rank):
                 "gpu_launches": launches,
                 "clocks": clocks,
                 "roofline": {"bound": "tensor", "achieved": fwd_tflops, "peak": peaks["burst"], "unit": "TFLOP/s",
-                             "frac": fwd_tflops / peaks["burst"], "traffic": None,
+                             "frac": fwd_tflops / peaks["burst"], "traffic": FWD_DRAM_BYTES.get(args.mode),
                              "kernel": "forward jet of the 15000-point off-surface cloud (C=5 channels), timed alone",
                              "ms": ms_fwd, "algorithmic_gflop": N_POINTS * FLOP_FWD_NONMNFLD / 1e9,
                              "peak_source": peaks["source"] + " bf16 dense burst",

@@ -52,7 +52,6 @@ static int check_mode(const DigsNet* net, int mode) {
 }
 static inline bool is_tc(int mode) { return mode != DIGS_MODE_FP32; }
 static inline int passes_of(int mode) { return mode == DIGS_MODE_BF16X2 ? 3 : 1; }
-static inline size_t max2(size_t a, size_t b) { return a > b ? a : b; }
 
 static PreSrc xyz_src(const DigsNet* net, const float* xyz, int64_t xyz_stride, const float* shape_bias, int64_t pps) {
     PreSrc s{};
