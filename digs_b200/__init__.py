@@ -7,8 +7,10 @@ All arithmetic runs in libdigs_b200.so (C-ABI in include/digs_b200.h); there is 
 """
 from .network import DiGSNetwork, Decoder, FCBlock, Sine
 from .losses import DiGSLoss
-from .grid import implicit2mesh, get_3d_grid, grid_axes, grid_query, slab_range
+from .grid import (implicit2mesh, get_3d_grid, grid_axes, grid_query, slab_range, compute_deriv_props,
+                   get_2d_grid_uniform)
 from .graph import GraphedStep
+from .optim import FusedClipAdam
 
 __all__ = ["DiGSNetwork", "Decoder", "FCBlock", "Sine", "DiGSLoss", "implicit2mesh", "get_3d_grid", "grid_axes",
-           "grid_query", "slab_range", "GraphedStep"]
+           "grid_query", "slab_range", "GraphedStep", "FusedClipAdam", "compute_deriv_props", "get_2d_grid_uniform"]

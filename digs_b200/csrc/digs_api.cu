@@ -242,4 +242,16 @@ int digs_grid_query(const DigsNet* net, const uint16_t* x_fp16, int nx, const ui
                             (cudaStream_t)stream);
 }
 
+int digs_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float max_norm, int step, float* scratch, void* stream) {
+    if (n < 0 || step < 1) { set_error("clip_adam: bad n/step"); return DIGS_EINVAL; }
+    if (n == 0) return DIGS_OK;
+    if (!params || !grads || !exp_avg || !exp_avg_sq || (max_norm > 0.f && !scratch)) {
+        set_error("clip_adam: NULL buffer");
+        return DIGS_EINVAL;
+    }
+    return clip_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, max_norm, step, scratch,
+                     (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -93,4 +93,8 @@ int loss_fused(const float* f_m, const float* g_m, int64_t nm, const float* f_n,
                float* fbar_m, float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n, float* terms_out,
                const float* weights_device, cudaStream_t st);
 
+// ---- optimizer tail (optim.cu) ------------------------------------------------------------------
+int clip_adam(float* p, float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float max_norm,
+              int step, float* scratch, cudaStream_t st);
+
 }  // namespace digs

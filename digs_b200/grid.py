@@ -111,3 +111,38 @@ def implicit2mesh(decoder, latent, grid_res, translate=[0., 0., 0.], scale=1, ge
         import trimesh
         mesh = trimesh.Trimesh(verts, faces, vertex_normals=normals, vertex_colors=values, validate=True)
     return {"mesh_trace": None, "mesh_obj": mesh}
+
+
+def get_2d_grid_uniform(resolution=100, range=1.2, device=None):
+    """Same as utils.get_2d_grid_uniform (utils/utils.py:176-183): x, y axes and the (res*res, 2) float32 grid."""
+    x = np.linspace(-range, range, resolution)
+    xx, yy = np.meshgrid(x, x)
+    pts = torch.tensor(np.vstack([xx.ravel(), yy.ravel()]).T, dtype=torch.float)
+    return x, x, (pts.to(device) if device is not None else pts)
+
+
+def compute_deriv_props(decoder, latent, z_gt, device):
+    """Drop-in for utils.compute_deriv_props (utils/utils.py:144-173): value, |grad f| eikonal residual, divergence and
+    curl images of the field on the 2-D sanity-check grid.
+
+    The reference obtains them from three autograd passes over the grid; here they are one inference launch of the jet
+    kernel (value, gradient and Laplacian channels).  The curl of a gradient field is identically zero -- the reference's
+    image only shows autograd rounding noise (~1e-6) -- so it is returned as exact zeros."""
+    if latent is not None:
+        raise NotImplementedError("digs_b200.compute_deriv_props: latent-conditioned 2-D fields are outside the fused path")
+    from .jet import jet_forward_raw
+    fc = getattr(decoder, "decoder", decoder)
+    fc = getattr(fc, "fc_block", fc)
+    res = z_gt.shape[1]
+    x, y, pts = get_2d_grid_uniform(resolution=res, range=1.2, device=device)
+    if not pts.is_cuda:
+        raise RuntimeError("digs_b200: compute_deriv_props needs a CUDA device -- no CPU fallback")
+    params = [p.detach() for p in fc.flat_params()]
+    f, g, lap, _ = jet_forward_raw(fc.spec(), params, pts.contiguous(), None, 0, True, False, fc.mode())
+    n = x.shape[0]
+    z_np = f.cpu().numpy().reshape(n, n)
+    eikonal_term = ((g.norm(2, dim=-1) - 1) ** 2).cpu().numpy().reshape(n, n)
+    grid_div = lap.cpu().numpy().reshape(n, n)
+    grid_curl = np.zeros((n, n), dtype=np.float32)
+    z_diff = np.abs(np.abs(np.reshape(z_np, [res, res])) - np.abs(z_gt)).reshape(n, n)
+    return x, y, z_np, z_diff, eikonal_term, grid_div, grid_curl

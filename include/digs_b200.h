@@ -147,6 +147,13 @@ int digs_grid_query(const DigsNet* net, const uint16_t* x_fp16, int nx, const ui
                     const float* shape_bias, float* sdf_out,
                     void* workspace, size_t workspace_bytes, int precision_mode, void* stream);
 
+/* Optimizer tail over flat buffers: clip_grad_norm_(params, max_norm) (train_surface_reconstruction.py:130; the loops
+ * hard-code 10.) followed by Adam.step() (train_surface_reconstruction.py:63,132).  grads are rescaled in place like
+ * clip_grad_norm_ does; max_norm <= 0 skips clipping (train_basic_shape.py:132-133 does not clip).  step is the 1-based
+ * Adam step count; scratch is one device float. */
+int digs_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float max_norm, int step, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

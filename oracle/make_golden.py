@@ -180,6 +180,19 @@ def main():
             grid["%s/values64" % tag] = net.double().decoder(gd["grid_points"].double()).numpy()[:, 0]
     np.savez_compressed(os.path.join(OUT, "grid.npz"), **grid)
 
+    # ---- 2-D derivative-field images (utils.compute_deriv_props, utils/utils.py:144-173) -------------------------------
+    deriv = {}
+    torch.manual_seed(INIT_SEED)
+    net2 = ref_digs.DiGSNetwork(latent_size=0, in_dim=2, decoder_hidden_dim=128, nl="sine", encoder_type="none",
+                                decoder_n_hidden_layers=4, init_type="mfgi")
+    z_gt = np.zeros((48, 48))
+    # (the reference builds the grid in float32 -- utils/utils.py:181 -- so only its fp32 run exists; the fp64 truth for
+    #  the test comes from oracle/jet_spec.py, itself pinned by the step fixtures)
+    x, y, z_np, z_diff, eik, div, curl = ref_utils.compute_deriv_props(net2.decoder, None, z_gt, None)
+    for k, v in (("x", x), ("z", z_np), ("z_diff", z_diff), ("eikonal", eik), ("div", div), ("curl", curl)):
+        deriv["f32/%s" % k] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, "deriv_props.npz"), **deriv)
+
     # ---- div-weight schedules ----------------------------------------------------------------------
     sched = {}
     for decay in ("linear", "quintic", "step", "none"):

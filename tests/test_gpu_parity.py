@@ -473,3 +473,52 @@ def test_sanity_config_2d(precision):
                           decoder_n_hidden_layers=4, init_type="mfgi"),
                      dict(weights=[3e3, 1e2, 1e2, 5e1, 1e2], loss_type="siren_wo_n_w_div", div_decay="linear",
                           div_type="l1", div_clamp=50), seed=23, bs=1, Nm=15000, Nn=15000, precision=precision, box=1.2)
+
+
+def test_compute_deriv_props_matches_reference_fixture():
+    """2-D derivative-field images (utils.compute_deriv_props): value, eikonal residual, divergence; curl == 0."""
+    g = golden("deriv_props.npz")
+    net = build_net(dict(latent_size=0, in_dim=2, decoder_hidden_dim=128, nl="sine", encoder_type="none",
+                         decoder_n_hidden_layers=4, init_type="mfgi"), 3627473).to(DEV)
+    z_gt = np.zeros((48, 48))
+    for precision in ("fp32", "bf16x2"):
+        net.precision = precision
+        x, y, z, z_diff, eik, div, curl = digs_b200.compute_deriv_props(net.decoder, None, z_gt, torch.device(DEV))
+        np.testing.assert_array_equal(x, g["f32/x"])
+        pts = np.stack(np.meshgrid(x, x), -1).reshape(-1, 2).astype(np.float32).astype(np.float64)
+        ref = jet_spec.forward(np_params(net, np.float64), pts, head_of(net))
+        tol = TOL[precision][0]
+        e32 = maxrel(g["f32/div"].reshape(-1), ref["lap"])      # the reference's own fp32 images vs fp64
+        assert maxrel(z.reshape(-1), ref["f"]) < max(tol, NOISE_MULT[precision] * maxrel(g["f32/z"].reshape(-1), ref["f"]))
+        assert maxrel(div.reshape(-1), ref["lap"]) < max(tol, NOISE_MULT[precision] * e32)
+        eik_ref = (np.linalg.norm(ref["grad"], axis=1) - 1) ** 2
+        assert maxrel(eik.reshape(-1), eik_ref) < max(2 * tol, NOISE_MULT[precision] * maxrel(g["f32/eikonal"].reshape(-1), eik_ref))
+        assert z.shape == (48, 48) and z_diff.shape == (48, 48) and not curl.any()
+    # the reference's curl image is autograd rounding noise around an exact zero
+    assert np.abs(g["f32/curl"]).max() < 1e-5 * np.abs(g["f32/div"]).max()
+
+
+@pytest.mark.parametrize("max_norm", [10.0, 0.0])
+def test_fused_clip_adam_matches_torch(max_norm):
+    """digs_clip_adam == torch.nn.utils.clip_grad_norm_(10) + torch.optim.Adam over several steps (the reference's tail)."""
+    torch.manual_seed(0)
+    ref_net = build_net(STEP_CASES["siren_l2_ragged"]["net"], 4).to(DEV)
+    our_net = build_net(STEP_CASES["siren_l2_ragged"]["net"], 4).to(DEV)
+    ref_opt = torch.optim.Adam(ref_net.parameters(), lr=5e-5, betas=(0.9, 0.999))
+    our_opt = digs_b200.FusedClipAdam(our_net.parameters(), lr=5e-5, betas=(0.9, 0.999), eps=1e-8, max_norm=max_norm)
+    assert list(our_net.state_dict().keys()) == list(ref_net.state_dict().keys())
+    for it in range(6):
+        gs = [torch.randn_like(p) * (50.0 if it % 2 else 0.01) for p in ref_net.parameters()]
+        for p, q, gr in zip(ref_net.parameters(), our_net.parameters(), gs):
+            p.grad = gr.clone()
+            q.grad.copy_(gr)
+        if max_norm > 0:
+            torch.nn.utils.clip_grad_norm_(ref_net.parameters(), max_norm)
+        ref_opt.step()
+        our_opt.step()
+        for p, q in zip(ref_net.parameters(), our_net.parameters()):
+            assert (p - q).abs().max() <= 2e-7 + 1e-5 * 5e-5, it
+            assert maxrel(q.grad.cpu(), p.grad.cpu()) < 1e-5          # gradients rescaled in place like clip_grad_norm_
+    # the drop-in network still runs on the re-pointed parameters
+    with torch.no_grad():
+        assert torch.isfinite(our_net.decoder(torch.rand(9, 3, device=DEV))).all()
