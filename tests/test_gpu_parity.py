@@ -522,3 +522,54 @@ def test_fused_clip_adam_matches_torch(max_norm):
     # the drop-in network still runs on the re-pointed parameters
     with torch.no_grad():
         assert torch.isfinite(our_net.decoder(torch.rand(9, 3, device=DEV))).all()
+
+
+def _edge_crossings(vol, axes):
+    """Zero-level edge crossings of a volume (nx,ny,nz) -- exactly the vertex set marching cubes emits (linear interpolation
+    along every grid edge with a sign change), which is all the vertex-based Chamfer distance of the reference's metrics
+    (compute_metrics_srb.py:38-57) depends on.  Third-party skimage.measure.marching_cubes itself is not installed."""
+    pts = []
+    grids = np.meshgrid(*axes, indexing="ij")
+    for ax in range(3):
+        a = np.moveaxis(vol, ax, 0)
+        v0, v1 = a[:-1], a[1:]
+        cross = (v0 * v1) < 0
+        t = v0[cross] / (v0[cross] - v1[cross])
+        comp = []
+        for k in range(3):
+            gk = np.moveaxis(grids[k], ax, 0)
+            comp.append(gk[:-1][cross] + t * (gk[1:][cross] - gk[:-1][cross]))
+        pts.append(np.stack(comp, 1))
+    return np.concatenate(pts, 0)
+
+
+def _chamfer(a, b):
+    from scipy.spatial import cKDTree
+    d1, _ = cKDTree(b).query(a, workers=-1)
+    d2, _ = cKDTree(a).query(b, workers=-1)
+    return 0.5 * (d1.mean() + d2.mean())              # compute_metrics_srb.py:38-57
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x2"])
+def test_extracted_surface_chamfer_unchanged_to_3_significant_figures(precision):
+    """north_star: 'Chamfer on the extracted mesh unchanged to 3 significant figures'.  Same surface extractor on the
+    reference-algorithm volume (fp32 CPU port) and on the kernel's volume, Chamfer of each against the same scan."""
+    case = STEP_CASES["c2_small"]
+    net = build_net(case["net"], case["seed"], precision=precision).to(DEV)
+    res = 96
+    axes, _, _ = grid_axes(res, np.array([[-1, 1], [-1, 1], [-1, 1]], dtype=float))
+    vol = grid_query(net, axes).cpu().numpy().transpose(1, 0, 2).astype(np.float64)          # (nx, ny, nz), utils/utils.py:349
+    a16 = [a.astype(np.float16).astype(np.float32) for a in axes]
+    xx, yy, zz = np.meshgrid(a16[0], a16[1], a16[2])                                          # reference point order
+    pts = torch.tensor(np.vstack([xx.ravel(), yy.ravel(), zz.ravel()]).T)
+    params = [p.detach().cpu() for p in net.decoder.fc_block.flat_params()]
+    ref = ref_autograd.grid_values(params, pts, head_of(net)).numpy()
+    ref_vol = ref.reshape(len(axes[1]), len(axes[0]), len(axes[2])).transpose(1, 0, 2).astype(np.float64)
+    rng = np.random.RandomState(0)
+    scan = rng.normal(size=(20000, 3))
+    scan = 0.5 * scan / np.linalg.norm(scan, axis=1, keepdims=True)                           # the "input scan": sphere r = 0.5
+    ours_pts, ref_pts = _edge_crossings(vol, axes), _edge_crossings(ref_vol, axes)
+    assert len(ours_pts) > 1000 and abs(len(ours_pts) - len(ref_pts)) <= 0.001 * len(ref_pts)
+    cd_ours, cd_ref = _chamfer(ours_pts, scan), _chamfer(ref_pts, scan)
+    assert abs(cd_ours - cd_ref) <= 5e-4 * cd_ref, (cd_ours, cd_ref)                          # 3 significant figures
+    assert _chamfer(ours_pts, ref_pts) < 0.02 * (axes[0][1] - axes[0][0])                     # surfaces coincide to 2 % of a cell
