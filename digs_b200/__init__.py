@@ -11,6 +11,7 @@ from .grid import (implicit2mesh, get_3d_grid, grid_axes, grid_query, slab_range
                    get_2d_grid_uniform)
 from .graph import GraphedStep
 from .optim import FusedClipAdam
+from .sampler import DeviceSampler
 
 __all__ = ["DiGSNetwork", "Decoder", "FCBlock", "Sine", "DiGSLoss", "implicit2mesh", "get_3d_grid", "grid_axes",
-           "grid_query", "slab_range", "GraphedStep", "FusedClipAdam", "compute_deriv_props", "get_2d_grid_uniform"]
+           "grid_query", "slab_range", "GraphedStep", "FusedClipAdam", "DeviceSampler", "compute_deriv_props", "get_2d_grid_uniform"]

@@ -242,6 +242,20 @@ int digs_grid_query(const DigsNet* net, const uint16_t* x_fp16, int nx, const ui
                             (cudaStream_t)stream);
 }
 
+int digs_sample_batch(const float* cloud, const float* normals, int64_t n_cloud, int d, int64_t n_pts, float box,
+                      uint64_t seed, uint64_t* iter_counter, float* mnfld, float* mnfld_normals, float* nonmnfld,
+                      void* stream) {
+    if (d != 2 && d != 3) { set_error("sample_batch: d must be 2 or 3"); return DIGS_EINVAL; }
+    if (n_cloud <= 0 || n_pts < 0 || n_pts > n_cloud) { set_error("sample_batch: need 0 <= n_pts <= n_cloud"); return DIGS_EINVAL; }
+    if (n_pts == 0) return DIGS_OK;
+    if (!cloud || !iter_counter || !mnfld || !nonmnfld || (normals && !mnfld_normals)) {
+        set_error("sample_batch: NULL buffer");
+        return DIGS_EINVAL;
+    }
+    return sample_batch(cloud, normals, n_cloud, d, n_pts, box, seed, reinterpret_cast<unsigned long long*>(iter_counter),
+                        mnfld, mnfld_normals, nonmnfld, (cudaStream_t)stream);
+}
+
 int digs_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                    float beta2, float eps, float max_norm, int step, float* scratch, void* stream) {
     if (n < 0 || step < 1) { set_error("clip_adam: bad n/step"); return DIGS_EINVAL; }

@@ -93,6 +93,10 @@ int loss_fused(const float* f_m, const float* g_m, int64_t nm, const float* f_n,
                float* fbar_m, float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n, float* terms_out,
                const float* weights_device, cudaStream_t st);
 
+// ---- on-device batch sampling (sampler.cu) -----------------------------------------------------
+int sample_batch(const float* cloud, const float* normals, int64_t n_cloud, int d, int64_t n_pts, float box, uint64_t seed,
+                 unsigned long long* iter_dev, float* mnfld, float* nrm, float* nonmnfld, cudaStream_t st);
+
 // ---- optimizer tail (optim.cu) ------------------------------------------------------------------
 int clip_adam(float* p, float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float max_norm,
               int step, float* scratch, cudaStream_t st);

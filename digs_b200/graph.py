@@ -20,7 +20,7 @@ from .dist import FlatGrads
 
 
 class GraphedStep:
-    def __init__(self, net, criterion, n_mnfld, n_nonmnfld, batch=1, flat=None, warmup=3):
+    def __init__(self, net, criterion, n_mnfld, n_nonmnfld, batch=1, flat=None, warmup=3, sampler=None):
         params = list(net.parameters())
         dev = params[0].device
         if dev.type != "cuda":
@@ -29,6 +29,9 @@ class GraphedStep:
             raise NotImplementedError("GraphedStep covers the single-shape recipes (encoder_type='none')")
         d = net.in_dim
         self.net, self.criterion = net, criterion
+        self.sampler = sampler          # optional digs_b200.DeviceSampler: the batch is then drawn INSIDE the graph
+        if sampler is not None and (batch != 1 or sampler.n_points != n_mnfld or n_mnfld != n_nonmnfld):
+            raise ValueError("GraphedStep: the sampler draws one cloud of n_points surface + n_points off-surface samples")
         self.flat = flat if flat is not None else FlatGrads(params, extra=8)
         net.decoder.fc_block.accumulate_grads_in_place = True
         self.mnfld = torch.zeros(batch, n_mnfld, d, device=dev).requires_grad_()
@@ -65,6 +68,8 @@ class GraphedStep:
         self._w_dev.copy_(slot, non_blocking=True)
 
     def _body(self):
+        if self.sampler is not None:
+            self.sampler.sample_into(self.mnfld, self.normals, self.nonmnfld)
         self.flat.zero_()
         out = self.net(self.nonmnfld, self.mnfld)
         loss_dict, _ = self.criterion(out, self.mnfld, self.nonmnfld, self.normals)
@@ -72,12 +77,14 @@ class GraphedStep:
         return loss_dict
 
     @torch.no_grad()
-    def step(self, mnfld_points, nonmnfld_points, mnfld_normals):
-        """Copies one batch into the static buffers, replays the graph.  Returns the dict of 8 loss tensors (static
-        device tensors, overwritten by the next call); parameter gradients are in `self.flat` / every `.grad`."""
-        self.mnfld.copy_(mnfld_points, non_blocking=True)
-        self.nonmnfld.copy_(nonmnfld_points, non_blocking=True)
-        self.normals.copy_(mnfld_normals, non_blocking=True)
+    def step(self, mnfld_points=None, nonmnfld_points=None, mnfld_normals=None):
+        """Copies one batch into the static buffers (or, with a sampler, lets the graph draw it), replays the graph.
+        Returns the dict of 8 loss tensors (static device tensors, overwritten by the next call); parameter gradients
+        are in `self.flat` / every `.grad`."""
+        if self.sampler is None:
+            self.mnfld.copy_(mnfld_points, non_blocking=True)
+            self.nonmnfld.copy_(nonmnfld_points, non_blocking=True)
+            self.normals.copy_(mnfld_normals, non_blocking=True)
         self._push_weights()
         self.graph.replay()
         return self.loss_dict

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--n_points", type=int, default=15000)
     ap.add_argument("--precision", default="bf16x2")
     ap.add_argument("--graph", action="store_true", help="GraphedStep + FusedClipAdam instead of eager autograd + torch Adam")
+    ap.add_argument("--device-sampler", action="store_true", help="with --graph: draw every batch on the device, inside the graph")
     ap.add_argument("--grid_res", type=int, default=128)
     args = ap.parse_args()
     dev = torch.device("cuda")
@@ -37,14 +38,16 @@ def main():
     decay = (1e2, 0.2, 1e2, 0.4, 0.0, 0.0)
     if args.graph:
         opt = DiGSNet.FusedClipAdam(net.parameters(), lr=5e-5, max_norm=10.0)
-        step = DiGSNet.GraphedStep(net, criterion, args.n_points, args.n_points, flat=opt.flat_grads)
+        sampler = DiGSNet.DeviceSampler(cloud, normals, args.n_points, grid_range=1.1, seed=0) if args.device_sampler else None
+        step = DiGSNet.GraphedStep(net, criterion, args.n_points, args.n_points, flat=opt.flat_grads, sampler=sampler)
     else:
         opt = torch.optim.Adam(net.parameters(), lr=5e-5, betas=(0.9, 0.999))
     t0 = time.time()
     for it in range(args.iters):
-        m, nrm, nm = (torch.from_numpy(a).to(dev) for a in synth.sample_batch(cloud, normals, args.n_points, seed=it))
+        if not (args.graph and args.device_sampler):
+            m, nrm, nm = (torch.from_numpy(a).to(dev) for a in synth.sample_batch(cloud, normals, args.n_points, seed=it))
         if args.graph:
-            loss_dict = step.step(m, nm, nrm)
+            loss_dict = step.step() if args.device_sampler else step.step(m, nm, nrm)
             opt.step()
         else:
             m.requires_grad_()

@@ -147,6 +147,15 @@ int digs_grid_query(const DigsNet* net, const uint16_t* x_fp16, int nx, const ui
                     const float* shape_bias, float* sdf_out,
                     void* workspace, size_t workspace_bytes, int precision_mode, void* stream);
 
+/* One iteration's batch, sampled on the device like ReconDataset.__getitem__ (recon_dataset.py:143-174) does on the host:
+ * n_pts distinct cloud points (+ normals, may be NULL) as the first n_pts entries of a fresh pseudo-random permutation,
+ * and n_pts points uniform in [-box, box]^d.  iter_counter: TWO device uint64 (iteration, ticket), zero-initialised by
+ * the caller; the kernel reads the iteration, derives that iteration's key from (seed, iteration) and increments it, so
+ * the call is CUDA-graph replayable.  The distribution, not numpy's RNG stream, is reproduced. */
+int digs_sample_batch(const float* cloud, const float* normals, int64_t n_cloud, int d, int64_t n_pts, float box,
+                      uint64_t seed, uint64_t* iter_counter, float* mnfld, float* mnfld_normals, float* nonmnfld,
+                      void* stream);
+
 /* Optimizer tail over flat buffers: clip_grad_norm_(params, max_norm) (train_surface_reconstruction.py:130; the loops
  * hard-code 10.) followed by Adam.step() (train_surface_reconstruction.py:63,132).  grads are rescaled in place like
  * clip_grad_norm_ does; max_norm <= 0 skips clipping (train_basic_shape.py:132-133 does not clip).  step is the 1-based

@@ -573,3 +573,31 @@ def test_extracted_surface_chamfer_unchanged_to_3_significant_figures(precision)
     cd_ours, cd_ref = _chamfer(ours_pts, scan), _chamfer(ref_pts, scan)
     assert abs(cd_ours - cd_ref) <= 5e-4 * cd_ref, (cd_ours, cd_ref)                          # 3 significant figures
     assert _chamfer(ours_pts, ref_pts) < 0.02 * (axes[0][1] - axes[0][0])                     # surfaces coincide to 2 % of a cell
+
+
+def test_device_sampler_distribution():
+    """digs_sample_batch reproduces ReconDataset.__getitem__ (recon_dataset.py:143-174) in distribution: distinct cloud
+    indices per batch (first n of a permutation), matching normals, uniform off-surface points, a new batch per call."""
+    from digs_b200 import synth
+    cloud, normals = synth.surface_cloud(100000, "torus", seed=0)
+    tag = cloud + 0.0
+    tag[:, 0] = np.arange(len(cloud))                 # make every cloud row identifiable through its first coordinate
+    s = digs_b200.DeviceSampler(tag, normals, 15000, grid_range=1.1, seed=7)
+    seen = []
+    for it in range(4):
+        m, nrm, nm = s.sample()
+        idx = m[0, :, 0].cpu().numpy().astype(np.int64)
+        assert len(np.unique(idx)) == 15000 and idx.min() >= 0 and idx.max() < 100000     # without replacement
+        np.testing.assert_array_equal(m[0, :, 1:].cpu().numpy(), tag[idx][:, 1:])
+        np.testing.assert_array_equal(nrm[0].cpu().numpy(), normals[idx])
+        u = nm[0].cpu().numpy()
+        assert u.min() >= -1.1 and u.max() <= 1.1
+        assert abs(u.mean()) < 0.02 and abs(u.var() - (2.2 ** 2) / 12) < 0.02             # uniform on [-1.1, 1.1]
+        assert abs(np.corrcoef(u[:, 0], u[:, 1])[0, 1]) < 0.03
+        # index coverage is uniform over the cloud: 10 equal bins
+        hist = np.histogram(idx, bins=10, range=(0, 100000))[0]
+        assert hist.min() > 1300 and hist.max() < 1700
+        seen.append(idx)
+    assert int(s.counter[0]) == 4
+    assert len(np.intersect1d(seen[0], seen[1])) < 0.3 * 15000                            # a fresh permutation every call
+    assert not np.array_equal(seen[0], seen[1])
