@@ -83,6 +83,7 @@ struct Cfg {
     static_assert(H == 128 || H == 256 || H == 512, "H must be 128, 256 or 512");
     static_assert(NCTX * CTX_COLS <= 512, "accumulators exceed TMEM");
     static_assert(EW % NUB == 0, "unit blocks must divide the epilogue warps of a context");
+    static_assert(NGRP >= GS, "every epilogue warp needs at least one point group (it arrives on b_ready after its last)");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
@@ -378,15 +379,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                             for (int c = 0; c < C; ++c)
 #pragma unroll
                                 for (int i = 0; i < GP; ++i) pre[c][i] = acc[c][i] + (c == 0 ? blv : 0.f);
-                            if (pl_l) {
-#pragma unroll
-                                for (int c = 0; c < C; ++c) {
-                                    float* dst = pl_l + c * plane_stride + goff;
-#pragma unroll
-                                    for (int i = 0; i < GP; ++i)
-                                        if (FULL || pg + i < a.n_pad) dst[i * H] = pre[c][i];
-                                }
-                            }
                         } else {
 #pragma unroll
                             for (int c = 0; c < C; ++c) {
@@ -462,39 +454,70 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                             for (int v = 0; v < P2; ++v) part[v] = (v < C * GP) ? out[v / GP][v % GP] * wl_u : 0.f;
                             warp_reduce_scatter<P2>(part, lane);
                             if (lane < C * GP) sHead[ub * N + (lane / GP) * T + g * GP + (lane % GP)] = part[0];
+                            if (pl_l) {        // the last sine layer's pre-activations are needed by the reverse pass too
+#pragma unroll
+                                for (int c = 0; c < C; ++c) {
+                                    float* dst = pl_l + c * plane_stride + goff;
+#pragma unroll
+                                    for (int i = 0; i < GP; ++i)
+                                        if (FULL || pg + i < a.n_pad) dst[i * H] = pre[c][i];
+                                }
+                            }
                         } else {
                             if (BWD) {
 #pragma unroll
                                 for (int i = 0; i < GP; ++i) bsum += out[0][i];
                             }
+                            // (1) next operand into shared memory first: it is what the MMA warp waits for
+                            uint32_t hiw[C][GP / 2], low[C][GP / 2];
 #pragma unroll
                             for (int c = 0; c < C; ++c) {
                                 const int ncol = c * T + g * GP;
-                                uint32_t hi[GP / 2], lo[GP / 2];
 #pragma unroll
-                                for (int i = 0; i < GP / 2; ++i) split2(out[c][2 * i], out[c][2 * i + 1], hi[i], lo[i]);
+                                for (int i = 0; i < GP / 2; ++i) split2(out[c][2 * i], out[c][2 * i + 1], hiw[c][i], low[c][i]);
                                 if constexpr (GP >= 8) {
 #pragma unroll
                                     for (int h = 0; h < GP / 8; ++h) {       // one 16-byte chunk per 8 points
                                         const int nc = ncol + 8 * h;
                                         const uint32_t off = rowoff + (uint32_t)(nc >> 6) * G::SN + (((((uint32_t)nc & 63) >> 3) << 4) ^ usw);
-                                        *reinterpret_cast<uint4*>(sB + off) = make_uint4(hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
+                                        *reinterpret_cast<uint4*>(sB + off) =
+                                            make_uint4(hiw[c][4 * h], hiw[c][4 * h + 1], hiw[c][4 * h + 2], hiw[c][4 * h + 3]);
                                         if constexpr (PASSES == 3)
                                             *reinterpret_cast<uint4*>(sB + G::B_PART + off) =
-                                                make_uint4(lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
+                                                make_uint4(low[c][4 * h], low[c][4 * h + 1], low[c][4 * h + 2], low[c][4 * h + 3]);
                                     }
                                 } else {
                                     const uint32_t off = rowoff + (uint32_t)(ncol >> 6) * G::SN +
                                                          (((((uint32_t)ncol & 63) >> 3) << 4) ^ usw) + (uint32_t)(ncol & 4) * 2;
-                                    *reinterpret_cast<uint2*>(sB + off) = make_uint2(hi[0], hi[1]);
-                                    if constexpr (PASSES == 3) *reinterpret_cast<uint2*>(sB + G::B_PART + off) = make_uint2(lo[0], lo[1]);
+                                    *reinterpret_cast<uint2*>(sB + off) = make_uint2(hiw[c][0], hiw[c][1]);
+                                    if constexpr (PASSES == 3)
+                                        *reinterpret_cast<uint2*>(sB + G::B_PART + off) = make_uint2(low[c][0], low[c][1]);
                                 }
-                                if (gp_l) {
-                                    // wgrad operand words (hi | lo << 16); forward tail points (>= n) must be exact zeros
+                            }
+                            // (2) this warp's last group of the step: release the MMA warp before the global stores
+                            if ((gi == G::GITER - 1) || (gpart + (gi + 1) * G::GS >= G::NGRP)) {
+                                fence_proxy_async();
+                                tc_fence_before();
+                                mbar_arrive(&b_ready[ctx]);
+                            }
+                            // (3) what the reverse pass / wgrad need, to HBM (128-byte lines per warp)
+                            if (!BWD && j > 0 && pl_l) {   // layer 0 is recomputed from the coordinates, never stored
+#pragma unroll
+                                for (int c = 0; c < C; ++c) {
+                                    float* dst = pl_l + c * plane_stride + goff;
+#pragma unroll
+                                    for (int i = 0; i < GP; ++i)
+                                        if (FULL || pg + i < a.n_pad) dst[i * H] = pre[c][i];
+                                }
+                            }
+                            if (gp_l) {
+                                // wgrad operand words (hi | lo << 16); forward tail points (>= n) must be exact zeros
+#pragma unroll
+                                for (int c = 0; c < C; ++c) {
                                     uint32_t* dst = gp_l + c * plane_stride + goff;
 #pragma unroll
                                     for (int i = 0; i < GP; ++i) {
-                                        uint32_t w = __byte_perm(hi[i >> 1], lo[i >> 1], (i & 1) ? 0x7632 : 0x5410);
+                                        uint32_t w = __byte_perm(hiw[c][i >> 1], low[c][i >> 1], (i & 1) ? 0x7632 : 0x5410);
                                         if constexpr (FULL) {
                                             dst[i * H] = w;
                                         } else {
@@ -517,11 +540,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                             if constexpr (D > 1) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 1, 30.f * w0s1);
                             if constexpr (D > 2) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 2, 30.f * w0s2);
                         }
-                    }
-                    if (!last) {
-                        fence_proxy_async();
-                        tc_fence_before();
-                        mbar_arrive(&b_ready[ctx]);
                     }
                 }
             };
