@@ -42,7 +42,7 @@ namespace tcpath {
 
 using namespace digs::tc;
 
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;
 constexpr int NTHREADS = EPI_WARPS * 32 + 64;
 constexpr int STAGES = 5;
 constexpr int STAGE_BYTES = 128 * 64 * 2;  // one A tile: 128 rows x 64 k, bf16
@@ -56,7 +56,7 @@ struct Cfg {
     // the operand fetch (not the tensor pipe) becomes the limit.  The code keeps the context machinery; NCTX stays 1.
     static constexpr int NCTX = 1;
     static constexpr int N = (H_ > 256) ? 64 : 128;   // UMMA N = operand columns per context (64 keeps X in smem at H=512)
-    static constexpr int GP = (C == 1) ? 16 : 8;      // points per epilogue group (one tcgen05.ld per channel)
+    static constexpr int GP = (C == 1) ? 16 : 4;      // points per epilogue group (one tcgen05.ld per channel)
     static constexpr int T = (N / C) / GP * GP;       // points per tile (whole groups)
     static constexpr int NGRP = T / GP;
     static constexpr int MT = H / 128;                // UMMA M tiles
@@ -72,7 +72,7 @@ struct Cfg {
     static constexpr int EW = EPI_WARPS / NCTX;       // epilogue warps per context
     static constexpr int ETHREADS = EW * 32;
     static constexpr int NUB = H / 32;                // 32-unit blocks
-    static constexpr int GS = (EW / NUB) > 0 ? (EW / NUB) : 1;
+    static constexpr int GS = EW / NUB;               // epilogue warps sharing one unit block (split over point groups)
     static constexpr int GITER = (NGRP + GS - 1) / GS;
     static constexpr int OFF_RING = NCTX * CTX_BYTES;
     static constexpr int OFF_XYZ = OFF_RING + STAGES * STAGE_BYTES;      // [NCTX][N*3] floats
@@ -82,7 +82,7 @@ struct Cfg {
     static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;               // + alignment slack
     static_assert(H == 128 || H == 256 || H == 512, "H must be 128, 256 or 512");
     static_assert(NCTX * CTX_COLS <= 512, "accumulators exceed TMEM");
-
+    static_assert(EW % NUB == 0, "unit blocks must divide the epilogue warps of a context");
     static_assert(NGRP >= GS, "every epilogue warp needs at least one point group (it arrives on b_ready after its last)");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -708,7 +708,7 @@ static int launch_h(const DigsNet* net, const CUtensorMap& tmap, const Args& a, 
     switch (net->H) {
         case 128: return launch<D, LAP, 128, PASSES, BWD>(tmap, a, st);
         case 256: return launch<D, LAP, 256, PASSES, BWD>(tmap, a, st);
-        // EXPERIMENT case 512 disabled
+        case 512: return launch<D, LAP, 512, PASSES, BWD>(tmap, a, st);
     }
     set_error("tc net: H=%d not supported (128, 256, 512)", net->H);
     return DIGS_ENOTIMPL;
