@@ -17,5 +17,8 @@ for _ in range(2):
     f, g, l, saved = djet.jet_forward_raw(fc.spec(), params, xyz, None, 0, True, True, fc.mode())
 for _ in range(2):
     djet.jet_backward_raw(fc.spec(), params, xyz, None, 0, True, torch.ones_like(f), torch.ones_like(g), torch.ones_like(f), saved, fc.mode())
+axes, _, _ = digs_b200.grid_axes(128, np.array([[-1, 1], [-1, 1], [-1, 1]], dtype=float))
+for _ in range(2):
+    digs_b200.grid_query(net, axes)
 torch.cuda.synchronize()
 print("ok")
