@@ -82,7 +82,7 @@ int forward(const DigsNet* net, const PreSrc& src, int64_t n, int want_jet, int 
 int backward(const DigsNet* net, const PreSrc& src, int64_t n, int want_lap, const float* f_bar, const float* g_bar,
              const float* l_bar, const void* saved, void* ws, const DigsGrads* grads, float* sb_grad, int passes,
              cudaStream_t st);
-int wgrad(const DigsNet* net, const __nv_bfloat16* GT, const __nv_bfloat16* actT, int C, int64_t n_pad,
+int wgrad(const DigsNet* net, const __nv_bfloat16* GP_words, const __nv_bfloat16* actP, int C, int64_t n_pad,
           const DigsGrads* grads, int passes, cudaStream_t st);
 }  // namespace tcpath
 

@@ -51,39 +51,43 @@ template <int D, int LAP, int H_, int PASSES>
 struct Cfg {
     static constexpr int C = 1 + D + LAP;
     static constexpr int H = H_;
-    // Tile contexts in flight per CTA.  Two 64-column contexts ping-ponging on the MMA warp were measured SLOWER than one
-    // 128-column context: a tcgen05.mma with N = 64 re-reads the 4 KB A tile from shared memory for half the math, and
-    // the operand fetch (not the tensor pipe) becomes the limit.  The code keeps the context machinery; NCTX stays 1.
-    static constexpr int NCTX = 1;
-    static constexpr int N = (H_ > 256) ? 64 : 128;   // UMMA N = operand columns per context (64 keeps X in smem at H=512)
+    // One tile context per CTA.  (Two 64-column contexts ping-ponging on the MMA warp were measured SLOWER: a
+    // tcgen05.mma with N = 64 re-reads the 4 KB A tile from shared memory for half the math, and the operand fetch,
+    // not the tensor pipe, becomes the limit.)
+    static constexpr int N = (H_ > 256) ? 64 : 128;   // UMMA N = operand columns per tile (64 keeps X in smem at H=512)
     static constexpr int GP = (C == 1) ? 16 : 4;      // points per epilogue group (one tcgen05.ld per channel)
     static constexpr int T = (N / C) / GP * GP;       // points per tile (whole groups)
     static constexpr int NGRP = T / GP;
     static constexpr int MT = H / 128;                // UMMA M tiles
+    // Operand phases: the epilogue finishes the units of the first MT/2 M tiles (= the first half of the next layer's K
+    // range) before it touches the rest, so the MMA warp starts the next layer on those K slabs while the epilogue
+    // is still working on the second half.  Accumulators are double-buffered in TMEM for that.
+    static constexpr int NPH = (MT >= 2) ? 2 : 1;
+    static constexpr int MTP = MT / NPH;              // M tiles per phase
+    static constexpr int WQ = EPI_WARPS / 4;          // epilogue warps per TMEM lane quarter
+    static constexpr int NITEMS = MTP * NGRP;         // (M tile, point group) work items per quarter and phase
+    static constexpr int ROT = WQ / 2;                // item rotation between phases (balances 6 items over 4 warps)
     static constexpr int NG = N / 64;                 // 64-column groups of the MN-major operand
     static constexpr int SN = 1024;                   // byte stride between column groups   (descriptor LBO)
     static constexpr int SK = NG * 1024;              // byte stride between 8-deep k groups (descriptor SBO)
     static constexpr int B_PART = (H / 8) * SK;       // bytes of one operand part (hi or lo)
     static constexpr int NPARTS = (PASSES == 3) ? 2 : 1;
-    static constexpr int CTX_BYTES = B_PART * NPARTS;
+    static constexpr int B_BYTES = B_PART * NPARTS;
     static constexpr int KSLABS = H / 64;
-    static constexpr int CTX_COLS = MT * N;           // TMEM columns per context
-    static constexpr int TMEM_COLS = (NCTX * CTX_COLS <= 128) ? 128 : ((NCTX * CTX_COLS <= 256) ? 256 : 512);
-    static constexpr int EW = EPI_WARPS / NCTX;       // epilogue warps per context
-    static constexpr int ETHREADS = EW * 32;
+    static constexpr int KS_PER_PH = KSLABS / NPH;
+    static constexpr int ACC_COLS = MT * N;           // TMEM columns of one accumulator buffer
+    static constexpr int TMEM_COLS = (2 * ACC_COLS <= 256) ? 256 : 512;
+    static constexpr int ETHREADS = EPI_WARPS * 32;
     static constexpr int NUB = H / 32;                // 32-unit blocks
-    static constexpr int GS = EW / NUB;               // epilogue warps sharing one unit block (split over point groups)
-    static constexpr int GITER = (NGRP + GS - 1) / GS;
-    static constexpr int OFF_RING = NCTX * CTX_BYTES;
-    static constexpr int OFF_XYZ = OFF_RING + STAGES * STAGE_BYTES;      // [NCTX][N*3] floats
-    static constexpr int OFF_HEAD = OFF_XYZ + NCTX * N * 3 * 4;           // [NCTX][NUB][N] floats
-    static constexpr int OFF_UBAR = OFF_HEAD + NCTX * NUB * N * 4;        // [NCTX][N] floats
-    static constexpr int OFF_BAR = OFF_UBAR + NCTX * N * 4;
+    static constexpr int OFF_RING = B_BYTES;
+    static constexpr int OFF_XYZ = OFF_RING + STAGES * STAGE_BYTES;      // [N*3] floats
+    static constexpr int OFF_HEAD = OFF_XYZ + N * 3 * 4;                  // [NUB][N] floats
+    static constexpr int OFF_UBAR = OFF_HEAD + NUB * N * 4;               // [N] floats
+    static constexpr int OFF_BAR = OFF_UBAR + N * 4;
     static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;               // + alignment slack
     static_assert(H == 128 || H == 256 || H == 512, "H must be 128, 256 or 512");
-    static_assert(NCTX * CTX_COLS <= 512, "accumulators exceed TMEM");
-    static_assert(EW % NUB == 0, "unit blocks must divide the epilogue warps of a context");
-    static_assert(NGRP >= GS, "every epilogue warp needs at least one point group (it arrives on b_ready after its last)");
+    static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
+    static_assert(NITEMS >= WQ, "every epilogue warp needs at least one item per phase (it arrives on b_ready after its last)");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
@@ -100,11 +104,11 @@ struct Args {
     float* f;                 // forward outputs
     float* grad;
     float* lap;
-    float* planes_t;          // forward: written (or NULL); reverse: read
-    __nv_bfloat16* actT;      // forward: written (or NULL)  (actP words)
+    float* planes;            // forward: written (or NULL); reverse: read
+    __nv_bfloat16* actP;      // forward: written (or NULL)
     float* head_saved;        // forward: written (or NULL)
     const float* ubar;        // reverse: [n][C] head adjoints (u_bar | gu_bar_k | lu_bar)
-    __nv_bfloat16* GT;        // reverse: written (GP words)
+    __nv_bfloat16* GP_words;  // reverse: written
     float* db[DIGS_MAX_LAYERS];  // reverse: bias gradients, layers 0..Lh (accumulated)
     float* dW0;               // reverse: (H, w0_stride), first d columns accumulated
     int w0_stride;
@@ -167,7 +171,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <int D, int LAP, int H, int PASSES, bool BWD>
 __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ CUtensorMap tmapW, Args a) {
     using G = Cfg<D, LAP, H, PASSES>;
-    constexpr int C = G::C, T = G::T, N = G::N, MT = G::MT, NCTX = G::NCTX;
+    constexpr int C = G::C, T = G::T, N = G::N, MT = G::MT, NPH = G::NPH;
     constexpr int GP = G::GP;
     constexpr int P2 = (C * GP <= 4) ? 4 : ((C * GP <= 16) ? 16 : 32);   // padded size of the head partial-sum vector
     extern __shared__ uint8_t smem_raw[];
@@ -176,14 +180,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
     uint64_t* w_full = bars;                          // [STAGES]
     uint64_t* w_empty = bars + STAGES;                // [STAGES]
-    uint64_t* b_ready = bars + 2 * STAGES;            // [NCTX] epilogue -> MMA: next operand complete (ETHREADS arrivals)
-    uint64_t* acc_ready = bars + 2 * STAGES + NCTX;   // [NCTX] MMA -> epilogue: accumulators complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NCTX);
+    uint64_t* b_ready = bars + 2 * STAGES;            // [2] epilogue -> MMA: operand rows of phase p complete (ETHREADS arrivals)
+    uint64_t* acc_ready = bars + 2 * STAGES + 2;      // MMA -> epilogue: accumulators of the step complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 3);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < NCTX; ++i) { mbar_init(&b_ready[i], G::ETHREADS); mbar_init(&acc_ready[i], 1); }
+        mbar_init(&b_ready[0], G::ETHREADS);
+        mbar_init(&b_ready[1], G::ETHREADS);
+        mbar_init(acc_ready, 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmapW);
     }
@@ -195,7 +201,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int64_t num_tiles = (a.n_pad + T - 1) / T;   // tiles cover [0, n_pad): the wgrad operands have no unwritten column
-    const int64_t num_rounds = (num_tiles + NCTX - 1) / NCTX;   // a round = NCTX consecutive tiles
     const int Lh = a.Lh;
 
     if (warp == EPI_WARPS) {
@@ -203,105 +208,97 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t r = blockIdx.x; r < num_rounds; r += gridDim.x)
+            for (int64_t r = blockIdx.x; r < num_tiles; r += gridDim.x)
                 for (int j = 0; j < Lh; ++j) {
                     const int l = BWD ? (Lh - j) : (j + 1);
-                    for (int ctx = 0; ctx < NCTX; ++ctx) {
-                        if (r * NCTX + ctx >= num_tiles) continue;
-                        for (int ks = 0; ks < G::KSLABS; ++ks)
-                            for (int m = 0; m < MT; ++m)
-                                for (int part = 0; part < G::NPARTS; ++part) {
-                                    mbar_wait(&w_empty[stage], phase ^ 1);
-                                    mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
-                                    // rows: [dir = fwd|transposed][part = hi|lo][layer][H]
-                                    tma_load_2d(sRing + stage * STAGE_BYTES, &tmapW, &w_full[stage], ks * 64,
-                                                (((BWD ? 2 : 0) + part) * Lh + (l - 1)) * H + m * 128);
-                                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                                }
-                    }
+                    for (int ks = 0; ks < G::KSLABS; ++ks)
+                        for (int m = 0; m < MT; ++m)
+                            for (int part = 0; part < G::NPARTS; ++part) {
+                                mbar_wait(&w_empty[stage], phase ^ 1);
+                                mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
+                                // rows: [dir = fwd|transposed][part = hi|lo][layer][H]
+                                tma_load_2d(sRing + stage * STAGE_BYTES, &tmapW, &w_full[stage], ks * 64,
+                                            (((BWD ? 2 : 0) + part) * Lh + (l - 1)) * H + m * 128);
+                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            }
                 }
         }
     } else if (warp == EPI_WARPS + 1) {
-        // ================= MMA issuer: alternates between the tile contexts ========================================
+        // ================= MMA issuer ===================================================================================
+        // Step j+1's accumulators go to TMEM buffer (j+1)&1; its K slabs of phase p start once b_ready[p] completes.
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, N, /*A K-major*/ 0, /*B MN-major*/ 1);
+            const uint32_t sB_hi = smem_u32(smem), sB_lo = sB_hi + G::B_PART;
             int stage = 0;
-            uint32_t phase = 0, pb[2] = {0, 0};
-            for (int64_t r = blockIdx.x; r < num_rounds; r += gridDim.x)
-                for (int j = 0; j < Lh; ++j)
-                    for (int ctx = 0; ctx < NCTX; ++ctx) {
-                        if (r * NCTX + ctx >= num_tiles) continue;
-                        const uint32_t sB_hi = smem_u32(smem) + ctx * G::CTX_BYTES, sB_lo = sB_hi + G::B_PART;
-                        mbar_wait(&b_ready[ctx], pb[ctx]);
-                        pb[ctx] ^= 1;
-                        tc_fence_after();
-                        for (int ks = 0; ks < G::KSLABS; ++ks)
-                            for (int m = 0; m < MT; ++m) {
-                                const uint32_t d_tmem = tmem_base + ctx * G::CTX_COLS + m * N;
-                                mbar_wait(&w_full[stage], phase);   // A_hi tile: hi*hi (+ hi*lo)
-                                tc_fence_after();
-                                {
-                                    const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
+            uint32_t phase = 0, pb = 0;
+            for (int64_t r = blockIdx.x; r < num_tiles; r += gridDim.x)
+                for (int j = 0; j < Lh; ++j) {
+                    const uint32_t d_buf = tmem_base + ((j + 1) & 1) * G::ACC_COLS;
+                    for (int ks = 0; ks < G::KSLABS; ++ks) {
+                        if (ks % G::KS_PER_PH == 0) {
+                            mbar_wait(&b_ready[ks / G::KS_PER_PH], pb);
+                            tc_fence_after();
+                        }
+                        for (int m = 0; m < MT; ++m) {
+                            const uint32_t d_tmem = d_buf + m * N;
+                            mbar_wait(&w_full[stage], phase);   // A_hi tile: hi*hi (+ hi*lo)
+                            tc_fence_after();
+                            {
+                                const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
 #pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk) {
-                                        uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
-                                        uint32_t koff = (ks * 8 + kk * 2) * G::SK;
-                                        uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
-                                        umma_bf16(d_tmem, da, db, idesc, (ks | kk) != 0);
-                                        if constexpr (PASSES == 3) {
-                                            uint64_t dbl = make_smem_desc(sB_lo + koff, G::SN, G::SK, LAYOUT_SW128);
-                                            umma_bf16(d_tmem, da, dbl, idesc, 1);
-                                        }
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
+                                    uint32_t koff = (ks * 8 + kk * 2) * G::SK;
+                                    uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
+                                    umma_bf16(d_tmem, da, db, idesc, (ks | kk) != 0);
+                                    if constexpr (PASSES == 3) {
+                                        uint64_t dbl = make_smem_desc(sB_lo + koff, G::SN, G::SK, LAYOUT_SW128);
+                                        umma_bf16(d_tmem, da, dbl, idesc, 1);
                                     }
+                                }
+                            }
+                            umma_commit(&w_empty[stage]);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            if constexpr (PASSES == 3) {
+                                mbar_wait(&w_full[stage], phase);   // A_lo tile: lo*hi
+                                tc_fence_after();
+                                const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
+                                    uint32_t koff = (ks * 8 + kk * 2) * G::SK;
+                                    uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
+                                    umma_bf16(d_tmem, da, db, idesc, 1);
                                 }
                                 umma_commit(&w_empty[stage]);
                                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                                if constexpr (PASSES == 3) {
-                                    mbar_wait(&w_full[stage], phase);   // A_lo tile: lo*hi
-                                    tc_fence_after();
-                                    const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
-#pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk) {
-                                        uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
-                                        uint32_t koff = (ks * 8 + kk * 2) * G::SK;
-                                        uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
-                                        umma_bf16(d_tmem, da, db, idesc, 1);
-                                    }
-                                    umma_commit(&w_empty[stage]);
-                                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                                }
                             }
-                        umma_commit(&acc_ready[ctx]);
+                        }
                     }
+                    pb ^= 1;               // both phase barriers complete exactly once per operand-producing step
+                    umma_commit(acc_ready);
+                }
         }
     } else {
-        // ================= epilogue warps: 8 (H <= 256) or 16 per context ============================================
-        const int ctx = warp / G::EW;
-        const int wl = warp % G::EW;               // warp index within the context's group
-        const int etid = tid - ctx * G::ETHREADS;  // thread index within the group
-        const int ub = wl % G::NUB;                // 32-unit block; ub % 4 == warp % 4 = TMEM lane quarter of this warp
-        const int gpart = wl / G::NUB;             // which share of the point groups
-        const int u = ub * 32 + lane;              // unit index
-        const int mt = ub >> 2;
-        const uint32_t t_base = tmem_base + ((uint32_t)((ub & 3) * 32) << 16) + ctx * G::CTX_COLS + mt * N;
-        uint8_t* sB = smem + ctx * G::CTX_BYTES;
-        float* sXyz = reinterpret_cast<float*>(smem + G::OFF_XYZ) + ctx * N * 3;
-        float* sHead = reinterpret_cast<float*>(smem + G::OFF_HEAD) + ctx * G::NUB * N;
-        float* sUbar = reinterpret_cast<float*>(smem + G::OFF_UBAR) + ctx * N;
+        // ================= epilogue warps ===============================================================================
+        // Warp w serves TMEM lane quarter q = w % 4 (hardware restriction) and shares that quarter's work items
+        // (M tile, point group) of each phase with the other WQ - 1 warps of the quarter.
+        const int q = warp & 3;
+        const int wr = warp >> 2;
+        uint8_t* sB = smem;
+        float* sXyz = reinterpret_cast<float*>(smem + G::OFF_XYZ);
+        float* sHead = reinterpret_cast<float*>(smem + G::OFF_HEAD);
+        float* sUbar = reinterpret_cast<float*>(smem + G::OFF_UBAR);
         uint32_t pa = 0;
-        const float4 w0v = __ldg(reinterpret_cast<const float4*>(a.w0_30) + u);
-        const float wl_u = __ldg(a.w_last + u);
-        const uint32_t rowoff = (uint32_t)(u >> 3) * G::SK + (uint32_t)(u & 7) * 128;
-        const uint32_t usw = (uint32_t)(u & 7) << 4;
+        const uint32_t usw = (uint32_t)(lane & 7) << 4;
         const int64_t plane_stride = a.n_pad * (int64_t)H;     // one (layer, channel) plane of `planes` / actP / GP
+        uint32_t* words = reinterpret_cast<uint32_t*>(BWD ? a.GP_words : a.actP);
 
-        for (int64_t r = blockIdx.x; r < num_rounds; r += gridDim.x) {
-            const int64_t tile = r * NCTX + ctx;
-            if (tile >= num_tiles) continue;       // whole group skips together (producer / MMA skip it too)
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int64_t p0 = tile * T;
             const bool full = (p0 + T <= a.n);     // no tail handling needed anywhere in this tile
             // ---- stage the tile's coordinates (and head adjoints) ----------------------------------------------------
-            for (int e = etid; e < T; e += G::ETHREADS) {
+            for (int e = tid; e < T; e += G::ETHREADS) {
                 int64_t gp = p0 + e;
                 if (gp >= a.n) gp = a.n - 1;
                 float x, y, z;
@@ -309,236 +306,239 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                 sXyz[e * 3] = x; sXyz[e * 3 + 1] = y; sXyz[e * 3 + 2] = z;
             }
             if constexpr (BWD) {
-                for (int e = etid; e < T * C; e += G::ETHREADS) {
+                for (int e = tid; e < T * C; e += G::ETHREADS) {
                     int64_t gp = p0 + e / C;
                     sUbar[e] = (gp < a.n) ? __ldg(a.ubar + gp * C + (e % C)) : 0.f;
                 }
             }
-            named_bar_sync(1 + ctx, G::ETHREADS);
-            // per-tile base pointers of this thread's unit column (point p0 + 4*gpart, channel 0, layer slot 0)
-            float* pl_tile = a.planes_t ? a.planes_t + (p0 + gpart * GP) * H + u : nullptr;
-            uint32_t* gp_tile = nullptr;
-            {
-                __nv_bfloat16* gq = BWD ? a.GT : a.actT;
-                if (gq) gp_tile = reinterpret_cast<uint32_t*>(gq) + (p0 + gpart * GP) * H + u;
-            }
+            named_bar_sync(1, G::ETHREADS);
 
             auto run_tile = [&](auto full_tag) {
                 constexpr bool FULL = decltype(full_tag)::value;
                 for (int j = 0; j <= Lh; ++j) {
                     const int l = BWD ? (Lh - j) : j;          // layer whose (pre-)activations this step touches
                     if (j > 0) {
-                        mbar_wait(&acc_ready[ctx], pa);
+                        mbar_wait(acc_ready, pa);
                         pa ^= 1;
                         tc_fence_after();
                     }
                     const bool last = (j == Lh);
-                    float bsum = 0.f, wlsum = 0.f, w0s0 = 0.f, w0s1 = 0.f, w0s2 = 0.f;
-                    float blv = 0.f;
-                    if (!BWD && j > 0) blv = __ldg(a.bias30 + (l - 1) * H + u);
+                    const uint32_t t_buf = tmem_base + ((uint32_t)(q * 32) << 16) + (j & 1) * G::ACC_COLS;
                     // layer slot bases: planes slot = l-1 (both directions); GP slot = l-1 (reverse), actP slot = l (forward)
-                    float* pl_l = pl_tile ? pl_tile + (int64_t)(l - 1) * C * plane_stride : nullptr;
-                    uint32_t* gp_l = gp_tile ? gp_tile + (int64_t)(BWD ? (l - 1) : l) * C * plane_stride : nullptr;
+                    float* pl_l = a.planes ? a.planes + (int64_t)(l - 1) * C * plane_stride + p0 * H : nullptr;
+                    uint32_t* wd_l = words ? words + (int64_t)(BWD ? (l - 1) : l) * C * plane_stride + p0 * H : nullptr;
 
-#pragma unroll
-                    for (int gi = 0; gi < G::GITER; ++gi) {
-                        const int g = gpart + gi * G::GS;
-                        if (G::GS > 1 && g >= G::NGRP) break;
-                        const int64_t pg = p0 + g * GP;              // first point of the group
-                        const int goff = gi * G::GS * GP * H;        // element offset of this group from the tile base pointers
-                        float acc[C][GP];                             // TMEM values: fwd pre-activations, bwd incoming adjoint
-                        if (j > 0) {
-#pragma unroll
-                            for (int c = 0; c < C; ++c) {
-                                if constexpr (GP == 16) tmem_ld16(t_base + c * T + g * GP, acc[c]);
-                                else if constexpr (GP == 8) tmem_ld8(t_base + c * T + g * GP, acc[c]);
-                                else tmem_ld4(t_base + c * T + g * GP, acc[c]);
-                            }
-                            tmem_ld_wait();
-                        }
-                        float pre[C][GP];                             // scaled pre-activations (30 z | 30 Z_k | 30 Q) of layer l
-                        if ((!BWD && j == 0) || (BWD && l == 0)) {
-#pragma unroll
-                            for (int i = 0; i < GP; ++i) {
-                                const float* xp = sXyz + (g * GP + i) * 3;
-                                float bz = w0v.w;
-                                if (a.src.shape_bias) {
-                                    int64_t gp = pg + i < a.n ? pg + i : a.n - 1;
-                                    bz = 30.f * __ldg(a.src.shape_bias + (gp / a.src.pps) * H + u);
-                                }
-                                pre[0][i] = fmaf(w0v.z, xp[2], fmaf(w0v.y, xp[1], fmaf(w0v.x, xp[0], bz)));
-                                if constexpr (D > 0) {
-                                    pre[1][i] = w0v.x;
-                                    if constexpr (D > 1) pre[2][i] = w0v.y;
-                                    if constexpr (D > 2) pre[3][i] = w0v.z;
-                                    if constexpr (LAP) pre[1 + D][i] = 0.f;
-                                }
-                            }
-                        } else if (!BWD) {
-#pragma unroll
-                            for (int c = 0; c < C; ++c)
-#pragma unroll
-                                for (int i = 0; i < GP; ++i) pre[c][i] = acc[c][i] + (c == 0 ? blv : 0.f);
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < C; ++c) {
-                                const float* srcp = pl_l + c * plane_stride + goff;
-#pragma unroll
-                                for (int i = 0; i < GP; ++i)
-                                    pre[c][i] = (FULL || pg + i < a.n_pad) ? __ldg(srcp + i * H) : 0.f;
-                            }
-                        }
-                        if (BWD && j == 0) {
-#pragma unroll
-                            for (int c = 0; c < C; ++c)
-#pragma unroll
-                                for (int i = 0; i < GP; ++i) acc[c][i] = sUbar[(g * GP + i) * C + c] * wl_u;
-                        }
-                        // ---------------- per-point jet math ------------------------------------------------------------
-                        float out[C][GP];  // fwd: layer outputs (h | A_k | P); bwd: scaled adjoints (zhat | Zhat_k | Qhat)
-#pragma unroll
-                        for (int i = 0; i < GP; ++i) {
-                            float s, c;
-                            sincos_reduced(pre[0][i], s, c);
-                            float S2 = 0.f;
-#pragma unroll
-                            for (int k = 0; k < D; ++k) S2 = fmaf(pre[1 + k][i], pre[1 + k][i], S2);
-                            const float Qp = LAP ? pre[C - 1][i] : 0.f;
-                            if (!BWD) {
-                                out[0][i] = s;
-#pragma unroll
-                                for (int k = 0; k < D; ++k) out[1 + k][i] = c * pre[1 + k][i];
-                                if constexpr (LAP) out[C - 1][i] = fmaf(c, Qp, -s * S2);
-                            } else {
-                                const float Pb = LAP ? acc[C - 1][i] : 0.f;
-                                float ZA = 0.f;
-#pragma unroll
-                                for (int k = 0; k < D; ++k) ZA = fmaf(pre[1 + k][i], acc[1 + k][i], ZA);
-                                if (j == 0) {
-                                    // dL/dw_last: ubar . (h | A_k | P) of the last sine layer
-                                    const float* ubp = sUbar + (g * GP + i) * C;
-                                    float t = ubp[0] * s;
-#pragma unroll
-                                    for (int k = 0; k < D; ++k) t = fmaf(ubp[1 + k], c * pre[1 + k][i], t);
-                                    if constexpr (LAP) t = fmaf(ubp[C - 1], fmaf(c, Qp, -s * S2), t);
-                                    wlsum += t;
-                                }
-                                float zh = c * acc[0][i] - s * ZA;
-                                if constexpr (LAP) zh -= Pb * fmaf(s, Qp, c * S2);
-                                out[0][i] = zh;
-#pragma unroll
-                                for (int k = 0; k < D; ++k) {
-                                    float v = c * acc[1 + k][i];
-                                    if constexpr (LAP) v -= 2.f * s * pre[1 + k][i] * Pb;
-                                    out[1 + k][i] = v;
-                                }
-                                if constexpr (LAP) out[C - 1][i] = c * Pb;
-                            }
-                        }
-                        // ---------------- scatter -----------------------------------------------------------------------
-                        if (BWD && l == 0) {
-                            // layer-0 parameter gradients: dW0[u][k] += 30 (zhat x_k + Zhat_k), db0[u] += 30 zhat
-#pragma unroll
-                            for (int i = 0; i < GP; ++i) {
-                                const float* xp = sXyz + (g * GP + i) * 3;
-                                bsum += out[0][i];
-                                if constexpr (D > 0) w0s0 += fmaf(out[0][i], xp[0], out[1][i]);
-                                if constexpr (D > 1) w0s1 += fmaf(out[0][i], xp[1], out[2][i]);
-                                if constexpr (D > 2) w0s2 += fmaf(out[0][i], xp[2], out[3][i]);
-                                if (a.sb_grad && pg + i < a.n)
-                                    atomicAdd(a.sb_grad + ((pg + i) / a.src.pps) * H + u, 30.f * out[0][i]);
-                            }
-                        } else if (!BWD && last) {
-                            float part[P2];
-#pragma unroll
-                            for (int v = 0; v < P2; ++v) part[v] = (v < C * GP) ? out[v / GP][v % GP] * wl_u : 0.f;
-                            warp_reduce_scatter<P2>(part, lane);
-                            if (lane < C * GP) sHead[ub * N + (lane / GP) * T + g * GP + (lane % GP)] = part[0];
-                            if (pl_l) {        // the last sine layer's pre-activations are needed by the reverse pass too
+#pragma unroll 1
+                    for (int ph = 0; ph < NPH; ++ph) {
+#pragma unroll 1
+                        for (int it = (wr + G::WQ - (ph * G::ROT) % G::WQ) % G::WQ; it < G::NITEMS; it += G::WQ) {
+                            const int mt = ph * G::MTP + it / G::NGRP;
+                            const int g = it % G::NGRP;
+                            const int ub = mt * 4 + q;                   // 32-unit block
+                            const int u = ub * 32 + lane;                // unit index
+                            const int64_t pg = p0 + g * GP;              // first point of the group
+                            const int goff = g * GP * H + u;             // element offset from the tile / layer base pointers
+                            const uint32_t t_base = t_buf + mt * N;
+                            float bsum = 0.f, wlsum = 0.f, w0s0 = 0.f, w0s1 = 0.f, w0s2 = 0.f;
+                            float acc[C][GP];                             // TMEM values: fwd pre-activations, bwd incoming adjoint
+                            if (j > 0) {
 #pragma unroll
                                 for (int c = 0; c < C; ++c) {
-                                    float* dst = pl_l + c * plane_stride + goff;
-#pragma unroll
-                                    for (int i = 0; i < GP; ++i)
-                                        if (FULL || pg + i < a.n_pad) dst[i * H] = pre[c][i];
+                                    if constexpr (GP == 16) tmem_ld16(t_base + c * T + g * GP, acc[c]);
+                                    else if constexpr (GP == 8) tmem_ld8(t_base + c * T + g * GP, acc[c]);
+                                    else tmem_ld4(t_base + c * T + g * GP, acc[c]);
                                 }
+                                tmem_ld_wait();
                             }
-                        } else {
-                            if (BWD) {
+                            float pre[C][GP];                             // scaled pre-activations (30 z | 30 Z_k | 30 Q) of layer l
+                            if ((!BWD && j == 0) || (BWD && l == 0)) {
+                                const float4 w0v = __ldg(reinterpret_cast<const float4*>(a.w0_30) + u);
 #pragma unroll
-                                for (int i = 0; i < GP; ++i) bsum += out[0][i];
-                            }
-                            // (1) next operand into shared memory first: it is what the MMA warp waits for
-                            uint32_t hiw[C][GP / 2], low[C][GP / 2];
-#pragma unroll
-                            for (int c = 0; c < C; ++c) {
-                                const int ncol = c * T + g * GP;
-#pragma unroll
-                                for (int i = 0; i < GP / 2; ++i) split2(out[c][2 * i], out[c][2 * i + 1], hiw[c][i], low[c][i]);
-                                if constexpr (GP >= 8) {
-#pragma unroll
-                                    for (int h = 0; h < GP / 8; ++h) {       // one 16-byte chunk per 8 points
-                                        const int nc = ncol + 8 * h;
-                                        const uint32_t off = rowoff + (uint32_t)(nc >> 6) * G::SN + (((((uint32_t)nc & 63) >> 3) << 4) ^ usw);
-                                        *reinterpret_cast<uint4*>(sB + off) =
-                                            make_uint4(hiw[c][4 * h], hiw[c][4 * h + 1], hiw[c][4 * h + 2], hiw[c][4 * h + 3]);
-                                        if constexpr (PASSES == 3)
-                                            *reinterpret_cast<uint4*>(sB + G::B_PART + off) =
-                                                make_uint4(low[c][4 * h], low[c][4 * h + 1], low[c][4 * h + 2], low[c][4 * h + 3]);
+                                for (int i = 0; i < GP; ++i) {
+                                    const float* xp = sXyz + (g * GP + i) * 3;
+                                    float bz = w0v.w;
+                                    if (a.src.shape_bias) {
+                                        int64_t gp = pg + i < a.n ? pg + i : a.n - 1;
+                                        bz = 30.f * __ldg(a.src.shape_bias + (gp / a.src.pps) * H + u);
                                     }
-                                } else {
-                                    const uint32_t off = rowoff + (uint32_t)(ncol >> 6) * G::SN +
-                                                         (((((uint32_t)ncol & 63) >> 3) << 4) ^ usw) + (uint32_t)(ncol & 4) * 2;
-                                    *reinterpret_cast<uint2*>(sB + off) = make_uint2(hiw[c][0], hiw[c][1]);
-                                    if constexpr (PASSES == 3)
-                                        *reinterpret_cast<uint2*>(sB + G::B_PART + off) = make_uint2(low[c][0], low[c][1]);
+                                    pre[0][i] = fmaf(w0v.z, xp[2], fmaf(w0v.y, xp[1], fmaf(w0v.x, xp[0], bz)));
+                                    if constexpr (D > 0) {
+                                        pre[1][i] = w0v.x;
+                                        if constexpr (D > 1) pre[2][i] = w0v.y;
+                                        if constexpr (D > 2) pre[3][i] = w0v.z;
+                                        if constexpr (LAP) pre[1 + D][i] = 0.f;
+                                    }
                                 }
-                            }
-                            // (2) this warp's last group of the step: release the MMA warp before the global stores
-                            if ((gi == G::GITER - 1) || (gpart + (gi + 1) * G::GS >= G::NGRP)) {
-                                fence_proxy_async();
-                                tc_fence_before();
-                                mbar_arrive(&b_ready[ctx]);
-                            }
-                            // (3) what the reverse pass / wgrad need, to HBM (128-byte lines per warp)
-                            if (!BWD && j > 0 && pl_l) {   // layer 0 is recomputed from the coordinates, never stored
+                            } else if (!BWD) {
+                                const float blv = __ldg(a.bias30 + (l - 1) * H + u);
+#pragma unroll
+                                for (int c = 0; c < C; ++c)
+#pragma unroll
+                                    for (int i = 0; i < GP; ++i) pre[c][i] = acc[c][i] + (c == 0 ? blv : 0.f);
+                            } else {
 #pragma unroll
                                 for (int c = 0; c < C; ++c) {
-                                    float* dst = pl_l + c * plane_stride + goff;
+                                    const float* srcp = pl_l + c * plane_stride + goff;
 #pragma unroll
                                     for (int i = 0; i < GP; ++i)
-                                        if (FULL || pg + i < a.n_pad) dst[i * H] = pre[c][i];
+                                        pre[c][i] = (FULL || pg + i < a.n_pad) ? __ldg(srcp + i * H) : 0.f;
                                 }
                             }
-                            if (gp_l) {
-                                // wgrad operand words (hi | lo << 16); forward tail points (>= n) must be exact zeros
+                            float wl_u = 0.f;
+                            if ((BWD && j == 0) || (!BWD && last)) wl_u = __ldg(a.w_last + u);
+                            if (BWD && j == 0) {
+#pragma unroll
+                                for (int c = 0; c < C; ++c)
+#pragma unroll
+                                    for (int i = 0; i < GP; ++i) acc[c][i] = sUbar[(g * GP + i) * C + c] * wl_u;
+                            }
+                            // ---------------- per-point jet math --------------------------------------------------------
+                            float out[C][GP];  // fwd: layer outputs (h | A_k | P); bwd: scaled adjoints (zhat | Zhat_k | Qhat)
+#pragma unroll
+                            for (int i = 0; i < GP; ++i) {
+                                float s, c;
+                                sincos_reduced(pre[0][i], s, c);
+                                float S2 = 0.f;
+#pragma unroll
+                                for (int k = 0; k < D; ++k) S2 = fmaf(pre[1 + k][i], pre[1 + k][i], S2);
+                                const float Qp = LAP ? pre[C - 1][i] : 0.f;
+                                if (!BWD) {
+                                    out[0][i] = s;
+#pragma unroll
+                                    for (int k = 0; k < D; ++k) out[1 + k][i] = c * pre[1 + k][i];
+                                    if constexpr (LAP) out[C - 1][i] = fmaf(c, Qp, -s * S2);
+                                } else {
+                                    const float Pb = LAP ? acc[C - 1][i] : 0.f;
+                                    float ZA = 0.f;
+#pragma unroll
+                                    for (int k = 0; k < D; ++k) ZA = fmaf(pre[1 + k][i], acc[1 + k][i], ZA);
+                                    if (j == 0) {
+                                        // dL/dw_last: ubar . (h | A_k | P) of the last sine layer
+                                        const float* ubp = sUbar + (g * GP + i) * C;
+                                        float t = ubp[0] * s;
+#pragma unroll
+                                        for (int k = 0; k < D; ++k) t = fmaf(ubp[1 + k], c * pre[1 + k][i], t);
+                                        if constexpr (LAP) t = fmaf(ubp[C - 1], fmaf(c, Qp, -s * S2), t);
+                                        wlsum += t;
+                                    }
+                                    float zh = c * acc[0][i] - s * ZA;
+                                    if constexpr (LAP) zh -= Pb * fmaf(s, Qp, c * S2);
+                                    out[0][i] = zh;
+#pragma unroll
+                                    for (int k = 0; k < D; ++k) {
+                                        float v = c * acc[1 + k][i];
+                                        if constexpr (LAP) v -= 2.f * s * pre[1 + k][i] * Pb;
+                                        out[1 + k][i] = v;
+                                    }
+                                    if constexpr (LAP) out[C - 1][i] = c * Pb;
+                                }
+                            }
+                            // ---------------- scatter -------------------------------------------------------------------
+                            if (BWD && l == 0) {
+                                // layer-0 parameter gradients: dW0[u][k] += 30 (zhat x_k + Zhat_k), db0[u] += 30 zhat
+#pragma unroll
+                                for (int i = 0; i < GP; ++i) {
+                                    const float* xp = sXyz + (g * GP + i) * 3;
+                                    bsum += out[0][i];
+                                    if constexpr (D > 0) w0s0 += fmaf(out[0][i], xp[0], out[1][i]);
+                                    if constexpr (D > 1) w0s1 += fmaf(out[0][i], xp[1], out[2][i]);
+                                    if constexpr (D > 2) w0s2 += fmaf(out[0][i], xp[2], out[3][i]);
+                                    if (a.sb_grad && pg + i < a.n)
+                                        atomicAdd(a.sb_grad + ((pg + i) / a.src.pps) * H + u, 30.f * out[0][i]);
+                                }
+                            } else if (!BWD && last) {
+                                float part[P2];
+#pragma unroll
+                                for (int v = 0; v < P2; ++v) part[v] = (v < C * GP) ? out[v / GP][v % GP] * wl_u : 0.f;
+                                warp_reduce_scatter<P2>(part, lane);
+                                if (lane < C * GP) sHead[ub * N + (lane / GP) * T + g * GP + (lane % GP)] = part[0];
+                                if (pl_l) {        // the last sine layer's pre-activations are needed by the reverse pass too
+#pragma unroll
+                                    for (int c = 0; c < C; ++c) {
+                                        float* dst = pl_l + c * plane_stride + goff;
+#pragma unroll
+                                        for (int i = 0; i < GP; ++i)
+                                            if (FULL || pg + i < a.n_pad) dst[i * H] = pre[c][i];
+                                    }
+                                }
+                            } else {
+                                if (BWD) {
+#pragma unroll
+                                    for (int i = 0; i < GP; ++i) bsum += out[0][i];
+                                }
+                                // (1) next operand into shared memory first: it is what the MMA warp waits for
+                                const uint32_t rowoff = (uint32_t)(u >> 3) * G::SK + (uint32_t)(u & 7) * 128;
+                                uint32_t hiw[C][GP / 2], low[C][GP / 2];
 #pragma unroll
                                 for (int c = 0; c < C; ++c) {
-                                    uint32_t* dst = gp_l + c * plane_stride + goff;
+                                    const int ncol = c * T + g * GP;
 #pragma unroll
-                                    for (int i = 0; i < GP; ++i) {
-                                        uint32_t w = __byte_perm(hiw[c][i >> 1], low[c][i >> 1], (i & 1) ? 0x7632 : 0x5410);
-                                        if constexpr (FULL) {
-                                            dst[i * H] = w;
-                                        } else {
-                                            if (!BWD && pg + i >= a.n) w = 0;
-                                            if (pg + i < a.n_pad) dst[i * H] = w;
+                                    for (int i = 0; i < GP / 2; ++i) split2(out[c][2 * i], out[c][2 * i + 1], hiw[c][i], low[c][i]);
+                                    if constexpr (GP >= 8) {
+#pragma unroll
+                                        for (int h = 0; h < GP / 8; ++h) {       // one 16-byte chunk per 8 points
+                                            const int nc = ncol + 8 * h;
+                                            const uint32_t off = rowoff + (uint32_t)(nc >> 6) * G::SN + (((((uint32_t)nc & 63) >> 3) << 4) ^ usw);
+                                            *reinterpret_cast<uint4*>(sB + off) =
+                                                make_uint4(hiw[c][4 * h], hiw[c][4 * h + 1], hiw[c][4 * h + 2], hiw[c][4 * h + 3]);
+                                            if constexpr (PASSES == 3)
+                                                *reinterpret_cast<uint4*>(sB + G::B_PART + off) =
+                                                    make_uint4(low[c][4 * h], low[c][4 * h + 1], low[c][4 * h + 2], low[c][4 * h + 3]);
+                                        }
+                                    } else {
+                                        const uint32_t off = rowoff + (uint32_t)(ncol >> 6) * G::SN +
+                                                             (((((uint32_t)ncol & 63) >> 3) << 4) ^ usw) + (uint32_t)(ncol & 4) * 2;
+                                        *reinterpret_cast<uint2*>(sB + off) = make_uint2(hiw[c][0], hiw[c][1]);
+                                        if constexpr (PASSES == 3)
+                                            *reinterpret_cast<uint2*>(sB + G::B_PART + off) = make_uint2(low[c][0], low[c][1]);
+                                    }
+                                }
+                                // (2) this warp's last item of the phase: release the MMA warp before the global stores
+                                if (it + G::WQ >= G::NITEMS) {
+                                    fence_proxy_async();
+                                    tc_fence_before();
+                                    mbar_arrive(&b_ready[ph]);
+                                }
+                                // (3) what the reverse pass / wgrad need, to HBM (128-byte lines per warp)
+                                if (!BWD && j > 0 && pl_l) {   // layer 0 is recomputed from the coordinates, never stored
+#pragma unroll
+                                    for (int c = 0; c < C; ++c) {
+                                        float* dst = pl_l + c * plane_stride + goff;
+#pragma unroll
+                                        for (int i = 0; i < GP; ++i)
+                                            if (FULL || pg + i < a.n_pad) dst[i * H] = pre[c][i];
+                                    }
+                                }
+                                if (wd_l) {
+                                    // wgrad operand words (hi | lo << 16); forward tail points (>= n) must be exact zeros
+#pragma unroll
+                                    for (int c = 0; c < C; ++c) {
+                                        uint32_t* dst = wd_l + c * plane_stride + goff;
+#pragma unroll
+                                        for (int i = 0; i < GP; ++i) {
+                                            uint32_t w = __byte_perm(hiw[c][i >> 1], low[c][i >> 1], (i & 1) ? 0x7632 : 0x5410);
+                                            if constexpr (FULL) {
+                                                dst[i * H] = w;
+                                            } else {
+                                                if (!BWD && pg + i >= a.n) w = 0;
+                                                if (pg + i < a.n_pad) dst[i * H] = w;
+                                            }
                                         }
                                     }
                                 }
                             }
-                        }
-                    }
-                    // ---------------- end of step ---------------------------------------------------------------------------
-                    if (BWD) {
-                        if (j == 0) atomicAdd(a.dw_last + u, wlsum);
-                        if (l >= 1) {
-                            atomicAdd(a.db[l] + u, 30.f * bsum);
-                        } else {
-                            if (!a.sb_grad) atomicAdd(a.db[0] + u, 30.f * bsum);
-                            if constexpr (D > 0) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 0, 30.f * w0s0);
-                            if constexpr (D > 1) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 1, 30.f * w0s1);
-                            if constexpr (D > 2) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 2, 30.f * w0s2);
+                            // ---------------- per-unit parameter gradients of this item ---------------------------------
+                            if (BWD) {
+                                if (j == 0) atomicAdd(a.dw_last + u, wlsum);
+                                if (l >= 1) {
+                                    atomicAdd(a.db[l] + u, 30.f * bsum);
+                                } else {
+                                    if (!a.sb_grad) atomicAdd(a.db[0] + u, 30.f * bsum);
+                                    if constexpr (D > 0) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 0, 30.f * w0s0);
+                                    if constexpr (D > 1) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 1, 30.f * w0s1);
+                                    if constexpr (D > 2) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 2, 30.f * w0s2);
+                                }
+                            }
                         }
                     }
                 }
@@ -548,8 +548,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
 
             if constexpr (!BWD) {
                 // ---- last layer: sum the per-unit-block partials, apply the output head ------------------------------
-                named_bar_sync(1 + ctx, G::ETHREADS);
-                for (int e = etid; e < T; e += G::ETHREADS) {
+                named_bar_sync(1, G::ETHREADS);
+                for (int e = tid; e < T; e += G::ETHREADS) {
                     int64_t gp = p0 + e;
                     if (gp < a.n) {
                         float v[C];
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                     }
                 }
             }
-            named_bar_sync(1 + ctx, G::ETHREADS);   // sXyz / sHead / sUbar are rewritten by the next tile
+            named_bar_sync(1, G::ETHREADS);   // sXyz / sHead / sUbar are rewritten by the next tile
         }
     }
     tc_fence_before();
@@ -670,7 +670,7 @@ size_t saved_bytes(const DigsNet* net, int64_t n, int want_lap) {
 }
 size_t bwd_ws_bytes(const DigsNet* net, int64_t n, int want_lap) {
     SavedLayout s = saved_layout(net, n, want_lap);
-    return prep_ws_bytes(net) + s.act_bytes /* GT */ + s.head_bytes /* ubar */;
+    return prep_ws_bytes(net) + s.act_bytes /* GP_words */ + s.head_bytes /* ubar */;
 }
 
 int num_sms() {
@@ -694,8 +694,7 @@ static int launch(const CUtensorMap& tmap, const Args& a, cudaStream_t st) {
         attr_set = true;
     }
     int64_t tiles = (a.n_pad + G::T - 1) / G::T;
-    int64_t rounds = (tiles + G::NCTX - 1) / G::NCTX;
-    int grid = (int)(rounds < num_sms() ? rounds : num_sms());
+    int grid = (int)(tiles < num_sms() ? tiles : num_sms());
     kern<<<grid, NTHREADS, G::SMEM_BYTES, st>>>(tmap, a);
     count_launch();
     cudaError_t e = cudaGetLastError();
@@ -772,8 +771,8 @@ int forward(const DigsNet* net, const PreSrc& src, int64_t n, int want_jet, int 
         SavedLayout s = saved_layout(net, n, want_lap);
         char* sp = reinterpret_cast<char*>(saved);
         a.n_pad = s.n_pad;
-        a.planes_t = reinterpret_cast<float*>(sp);
-        a.actT = reinterpret_cast<__nv_bfloat16*>(sp + s.planes_bytes);
+        a.planes = reinterpret_cast<float*>(sp);
+        a.actP = reinterpret_cast<__nv_bfloat16*>(sp + s.planes_bytes);
         a.head_saved = reinterpret_cast<float*>(sp + s.planes_bytes + s.act_bytes);
     } else {
         a.n_pad = (n + 7) / 8 * 8;
@@ -781,18 +780,18 @@ int forward(const DigsNet* net, const PreSrc& src, int64_t n, int want_jet, int 
     return dispatch<false>(net, tmap, a, want_jet, want_lap, passes, st);
 }
 
-// Reverse pass: head adjoint (fp32 kernel) -> fused dgrad kernel (bias / layer-0 / last-layer gradients, GT) -> wgrad GEMMs.
+// Reverse pass: head adjoint (fp32 kernel) -> fused dgrad kernel (bias / layer-0 / last-layer gradients, GP_words) -> wgrad GEMMs.
 int backward(const DigsNet* net, const PreSrc& src, int64_t n, int want_lap, const float* f_bar, const float* g_bar,
              const float* l_bar, const void* saved, void* ws, const DigsGrads* grads, float* sb_grad, int passes,
              cudaStream_t st) {
     if (n == 0) return DIGS_OK;
     SavedLayout s = saved_layout(net, n, want_lap);
     const char* sp = reinterpret_cast<const char*>(saved);
-    float* planes_t = reinterpret_cast<float*>(const_cast<char*>(sp));
-    __nv_bfloat16* actT = reinterpret_cast<__nv_bfloat16*>(const_cast<char*>(sp) + s.planes_bytes);
+    float* planes = reinterpret_cast<float*>(const_cast<char*>(sp));
+    __nv_bfloat16* actP = reinterpret_cast<__nv_bfloat16*>(const_cast<char*>(sp) + s.planes_bytes);
     const float* head_saved = reinterpret_cast<const float*>(sp + s.planes_bytes + s.act_bytes);
     char* w = reinterpret_cast<char*>(ws);
-    __nv_bfloat16* GT = reinterpret_cast<__nv_bfloat16*>(w + prep_ws_bytes(net));
+    __nv_bfloat16* GP_words = reinterpret_cast<__nv_bfloat16*>(w + prep_ws_bytes(net));
     float* ubar = reinterpret_cast<float*>(w + prep_ws_bytes(net) + s.act_bytes);
     int rc = simt::head_seed(net, n, want_lap, head_saved, f_bar, g_bar, l_bar, ubar, grads->db[net->Lh + 1], st);
     if (rc) return rc;
@@ -803,9 +802,9 @@ int backward(const DigsNet* net, const PreSrc& src, int64_t n, int want_lap, con
     a.src = src;
     a.n = n;
     a.n_pad = s.n_pad;
-    a.planes_t = planes_t;
+    a.planes = planes;
     a.ubar = ubar;
-    a.GT = GT;
+    a.GP_words = GP_words;
     for (int l = 0; l <= net->Lh; ++l) a.db[l] = grads->db[l];
     a.dW0 = grads->dW[0];
     a.w0_stride = net->w0_stride;
@@ -813,7 +812,7 @@ int backward(const DigsNet* net, const PreSrc& src, int64_t n, int want_lap, con
     a.sb_grad = sb_grad;
     rc = dispatch<true>(net, tmap, a, 1, want_lap, passes, st);
     if (rc) return rc;
-    return wgrad(net, GT, actT, s.C, s.n_pad, grads, passes, st);
+    return wgrad(net, GP_words, actP, s.C, s.n_pad, grads, passes, st);
 }
 
 }  // namespace tcpath

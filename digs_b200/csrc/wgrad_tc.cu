@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(const __grid_constan
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-int wgrad(const DigsNet* net, const __nv_bfloat16* GT, const __nv_bfloat16* actT, int C, int64_t n_pad,
+int wgrad(const DigsNet* net, const __nv_bfloat16* GP_words, const __nv_bfloat16* actP, int C, int64_t n_pad,
           const DigsGrads* grads, int passes, cudaStream_t st) {
     (void)passes;   // both operands always carry hi and lo
     EncodeFn enc = get_encode();
@@ -156,10 +156,10 @@ int wgrad(const DigsNet* net, const __nv_bfloat16* GT, const __nv_bfloat16* actT
     cuuint64_t gstr[2] = {(cuuint64_t)H * 4, (cuuint64_t)kcols * H * 4};
     cuuint32_t estr[3] = {1, 1, 1};
     cuuint32_t box[3] = {64, 64, 1};
-    CUresult r1 = enc(&tG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(GT), gdim, gstr, box, estr,
+    CUresult r1 = enc(&tG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(GP_words), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CUresult r2 = enc(&tA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(actT), gdim, gstr, box, estr,
+    CUresult r2 = enc(&tA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(actP), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(wgrad) failed (%d, %d)", (int)r1, (int)r2); return DIGS_ECUDA; }
