@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
     constexpr int GP = G::GP;
     constexpr int P2 = (C * GP <= 4) ? 4 : ((C * GP <= 16) ? 16 : 32);   // padded size of the head partial-sum vector
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still a shared-space pointer
     uint8_t* sRing = smem + G::OFF_RING;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
     uint64_t* w_full = bars;                          // [STAGES]
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
         // (M tile, point group) of each phase with the other WQ - 1 warps of the quarter.
         const int q = warp & 3;
         const int wr = warp >> 2;
-        uint8_t* sB = smem;
+        const uint32_t sB = smem_u32(smem);        // operand stores use shared-space addresses (st.shared)
         float* sXyz = reinterpret_cast<float*>(smem + G::OFF_XYZ);
         float* sHead = reinterpret_cast<float*>(smem + G::OFF_HEAD);
         float* sUbar = reinterpret_cast<float*>(smem + G::OFF_UBAR);
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
 #pragma unroll
                                 for (int c = 0; c < C; ++c)
 #pragma unroll
-                                    for (int i = 0; i < GP; ++i) pre[c][i] = acc[c][i] + (c == 0 ? blv : 0.f);
+                                    for (int i = 0; i < GP; ++i) pre[c][i] = (c == 0) ? acc[c][i] + blv : acc[c][i];
                             } else {
 #pragma unroll
                                 for (int c = 0; c < C; ++c) {
@@ -479,18 +479,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                                         for (int h = 0; h < GP / 8; ++h) {       // one 16-byte chunk per 8 points
                                             const int nc = ncol + 8 * h;
                                             const uint32_t off = rowoff + (uint32_t)(nc >> 6) * G::SN + (((((uint32_t)nc & 63) >> 3) << 4) ^ usw);
-                                            *reinterpret_cast<uint4*>(sB + off) =
-                                                make_uint4(hiw[c][4 * h], hiw[c][4 * h + 1], hiw[c][4 * h + 2], hiw[c][4 * h + 3]);
+                                            sts_v4(sB + off, hiw[c][4 * h], hiw[c][4 * h + 1], hiw[c][4 * h + 2], hiw[c][4 * h + 3]);
                                             if constexpr (PASSES == 3)
-                                                *reinterpret_cast<uint4*>(sB + G::B_PART + off) =
-                                                    make_uint4(low[c][4 * h], low[c][4 * h + 1], low[c][4 * h + 2], low[c][4 * h + 3]);
+                                                sts_v4(sB + G::B_PART + off, low[c][4 * h], low[c][4 * h + 1], low[c][4 * h + 2], low[c][4 * h + 3]);
                                         }
                                     } else {
                                         const uint32_t off = rowoff + (uint32_t)(ncol >> 6) * G::SN +
                                                              (((((uint32_t)ncol & 63) >> 3) << 4) ^ usw) + (uint32_t)(ncol & 4) * 2;
-                                        *reinterpret_cast<uint2*>(sB + off) = make_uint2(hiw[c][0], hiw[c][1]);
-                                        if constexpr (PASSES == 3)
-                                            *reinterpret_cast<uint2*>(sB + G::B_PART + off) = make_uint2(low[c][0], low[c][1]);
+                                        sts_v2(sB + off, hiw[c][0], hiw[c][1]);
+                                        if constexpr (PASSES == 3) sts_v2(sB + G::B_PART + off, low[c][0], low[c][1]);
                                     }
                                 }
                                 // (2) this warp's last item of the phase: release the MMA warp before the global stores
