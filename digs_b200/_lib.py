@@ -40,6 +40,7 @@ EXPORTS = (
     "digs_abi_version", "digs_last_error", "digs_launch_count", "digs_saved_bytes", "digs_forward_workspace_bytes",
     "digs_backward_workspace_bytes", "digs_value_workspace_bytes", "digs_grid_workspace_bytes",
     "digs_jet_forward", "digs_jet_backward", "digs_loss_fused", "digs_loss_fused_dw", "digs_value_forward", "digs_grid_query", "digs_clip_adam", "digs_sample_batch",
+    "digs_mt_classify", "digs_mt_emit", "digs_nn_query",
 )
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdigs_b200.so")
@@ -90,6 +91,13 @@ def lib():
                                  ctypes.c_float, i32, vp, vp]
     L.digs_sample_batch.restype = i32
     L.digs_sample_batch.argtypes = [vp, vp, i64, i32, i64, ctypes.c_float, ctypes.c_uint64, vp, vp, vp, vp, vp]
+    L.digs_mt_classify.restype = i32
+    L.digs_mt_classify.argtypes = [vp, i32, i32, i32, ctypes.c_float, vp, vp, vp]
+    L.digs_mt_emit.restype = i32
+    L.digs_mt_emit.argtypes = [vp, i32, i32, i32, ctypes.c_float, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float),
+                               ctypes.POINTER(ctypes.c_float), vp, vp, vp, vp, vp, vp, vp, vp]
+    L.digs_nn_query.restype = i32
+    L.digs_nn_query.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp]
     if L.digs_abi_version() != 1:
         raise RuntimeError("digs_b200: ABI version mismatch")
     _lib = L

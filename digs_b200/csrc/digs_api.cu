@@ -256,6 +256,29 @@ int digs_sample_batch(const float* cloud, const float* normals, int64_t n_cloud,
                         mnfld, mnfld_normals, nonmnfld, (cudaStream_t)stream);
 }
 
+int digs_mt_classify(const float* vol, int n0, int n1, int n2, float level, uint8_t* edge_flags, uint8_t* tri_counts,
+                     void* stream) {
+    if (!vol || !edge_flags || !tri_counts) { set_error("mt_classify: NULL buffer"); return DIGS_EINVAL; }
+    return mesh::classify(vol, n0, n1, n2, level, edge_flags, tri_counts, (cudaStream_t)stream);
+}
+
+int digs_mt_emit(const float* vol, int n0, int n1, int n2, float level, const int* axis_of, const float* origin,
+                 const float* spacing, const uint8_t* edge_flags, const uint8_t* tri_counts, const int32_t* vert_offsets,
+                 const int32_t* tri_offsets, float* verts, float* normals, int32_t* faces, void* stream) {
+    if (!vol || !axis_of || !origin || !spacing || !edge_flags || !vert_offsets) { set_error("mt_emit: NULL buffer"); return DIGS_EINVAL; }
+    if (faces && (!tri_counts || !tri_offsets)) { set_error("mt_emit: faces need tri_counts and tri_offsets"); return DIGS_EINVAL; }
+    if (normals && !verts) { set_error("mt_emit: normals are written together with verts"); return DIGS_EINVAL; }
+    return mesh::emit(vol, n0, n1, n2, level, axis_of, origin, spacing, edge_flags, tri_counts, vert_offsets, tri_offsets,
+                      verts, normals, faces, (cudaStream_t)stream);
+}
+
+int digs_nn_query(const float* ref, int64_t n_ref, const float* query, int64_t n_query, int d, float* dist, int32_t* idx,
+                  void* stream) {
+    if (n_query < 0) { set_error("nn_query: negative n_query"); return DIGS_EINVAL; }
+    if (n_query > 0 && (!ref || !query || !dist)) { set_error("nn_query: NULL buffer"); return DIGS_EINVAL; }
+    return mesh::nn_query(ref, n_ref, query, n_query, d, dist, idx, (cudaStream_t)stream);
+}
+
 int digs_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                    float beta2, float eps, float max_norm, int step, float* scratch, void* stream) {
     if (n < 0 || step < 1) { set_error("clip_adam: bad n/step"); return DIGS_EINVAL; }

@@ -101,4 +101,13 @@ int sample_batch(const float* cloud, const float* normals, int64_t n_cloud, int 
 int clip_adam(float* p, float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float max_norm,
               int step, float* scratch, cudaStream_t st);
 
+// ---- iso-surface extraction and nearest neighbours (mesh.cu) ------------------------------------
+namespace mesh {
+int classify(const float* vol, int n0, int n1, int n2, float level, uint8_t* flags, uint8_t* ntri, cudaStream_t st);
+int emit(const float* vol, int n0, int n1, int n2, float level, const int* axis_of, const float* origin, const float* spacing,
+         const uint8_t* flags, const uint8_t* ntri, const int32_t* voff, const int32_t* toff, float* verts, float* normals,
+         int32_t* faces, cudaStream_t st);
+int nn_query(const float* ref, int64_t nr, const float* qry, int64_t nq, int d, float* dist, int32_t* idx, cudaStream_t st);
+}  // namespace mesh
+
 }  // namespace digs

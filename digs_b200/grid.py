@@ -60,8 +60,7 @@ def grid_query(decoder, axes, latent=None, iy_range=None, device=None, out=None)
     fc = getattr(decoder, "decoder", decoder)
     fc = getattr(fc, "fc_block", fc)
     params = [p.detach() for p in fc.flat_params()]
-    if device is None:
-        device = params[0].device
+    device = params[0].device if device is None else torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("digs_b200: grid_query needs the network on a CUDA device -- no CPU fallback")
     spec = fc.spec()
@@ -92,24 +91,21 @@ def implicit2mesh(decoder, latent, grid_res, translate=[0., 0., 0.], scale=1, ge
                   bbox=np.array([[-1, 1], [-1, 1], [-1, 1]])):
     """Same signature / return value as utils.implicit2mesh (utils/utils.py:329-370).
 
-    The SDF volume comes from the fused grid kernel; marching cubes and the mesh container stay with the
-    third-party packages the reference uses (skimage, trimesh) and are imported lazily."""
+    The SDF volume comes from the fused grid kernel and stays in HBM; the zero level set is extracted there by
+    `digs_b200.mesh.marching_tets` (the reference hands a float64 host copy to skimage's marching cubes,
+    utils/utils.py:349-355) with the reference's spacing (one cell width for all axes), origin, scale and translate
+    (utils/utils.py:355-358).  `mesh_obj` is a `digs_b200.mesh.TriMesh` (vertices / faces / vertex_normals /
+    export(path, vertex_normal=True)) instead of a trimesh.Trimesh."""
+    from .mesh import marching_tets, TriMesh
     axes, _, _ = grid_axes(grid_res, bbox)
-    cell_width = axes[0][2] - axes[0][1]
-    vol = grid_query(decoder, axes, latent=latent, device=device)
-    z = vol.cpu().numpy().transpose([1, 0, 2]).astype(np.float64)      # (nx, ny, nz), utils/utils.py:349-350
-    try:
-        from skimage import measure
-    except ImportError as exc:                                          # pragma: no cover
-        raise RuntimeError("implicit2mesh needs scikit-image for marching cubes (utils/utils.py:354)") from exc
-    verts, faces, normals, values = measure.marching_cubes(volume=z, level=0.0,
-                                                           spacing=(cell_width, cell_width, cell_width))
-    verts = verts + np.array([axes[0][0], axes[1][0], axes[2][0]])
-    verts = verts * (1 / scale) - translate
-    mesh = None
-    if get_mesh:
-        import trimesh
-        mesh = trimesh.Trimesh(verts, faces, vertex_normals=normals, vertex_colors=values, validate=True)
+    cell_width = float(axes[0][2] - axes[0][1])
+    vol = grid_query(decoder, axes, latent=latent, device=device)       # flat [iy][ix][iz]
+    nx, ny, nz = (len(a) for a in axes)
+    verts, faces, normals = marching_tets(vol.view(ny, nx, nz), level=0.0, spacing=(cell_width,) * 3,
+                                          origin=(float(axes[1][0]), float(axes[0][0]), float(axes[2][0])),
+                                          axis_of=(1, 0, 2))
+    verts = verts * (1.0 / scale) - torch.as_tensor(np.asarray(translate, dtype=np.float32), device=verts.device)
+    mesh = TriMesh(verts, faces, normals) if get_mesh else None
     return {"mesh_trace": None, "mesh_obj": mesh}
 
 

@@ -163,6 +163,30 @@ int digs_sample_batch(const float* cloud, const float* normals, int64_t n_cloud,
 int digs_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                    float beta2, float eps, float max_norm, int step, float* scratch, void* stream);
 
+/* Iso-surface extraction on a dense fp32 volume in memory order (n0, n1, n2), n2 fastest: replaces
+ * skimage.measure.marching_cubes(volume, level, spacing) + the origin shift of utils/utils.py:354-358.  Vertices sit on
+ * the grid edges whose endpoint values straddle `level`, at the linear interpolation point (the marching-cubes vertex
+ * rule); cells are triangulated by marching tetrahedra on the Kuhn split (watertight, no case tables), so edges also
+ * include face and body diagonals.
+ *   digs_mt_classify: edge_flags[p] = 7-bit mask of straddling edges that start at grid point p (bit m-1 <-> offset
+ *     ((m>>2)&1, (m>>1)&1, m&1) along (axis0, axis1, axis2)); tri_counts[p] = triangles of the cell starting at p.
+ *   The caller forms EXCLUSIVE prefix sums vert_offsets = scan(popcount(edge_flags)), tri_offsets = scan(tri_counts).
+ *   digs_mt_emit: verts (V,3), unit normals (V,3; NULL to skip; normalised volume gradient, pointing to larger values),
+ *     faces (F,3) int32 vertex ids, oriented so the face normal points to larger values.  Memory axis k is logical axis
+ *     axis_of[k] (a permutation of 0,1,2; the reference's volume is [iy][ix][iz] -> {1,0,2}); position along it is
+ *     origin[k] + spacing[k] * index.  axis_of / origin / spacing are HOST arrays of 3. */
+int digs_mt_classify(const float* vol, int n0, int n1, int n2, float level, uint8_t* edge_flags, uint8_t* tri_counts,
+                     void* stream);
+int digs_mt_emit(const float* vol, int n0, int n1, int n2, float level, const int* axis_of, const float* origin,
+                 const float* spacing, const uint8_t* edge_flags, const uint8_t* tri_counts, const int32_t* vert_offsets,
+                 const int32_t* tri_offsets, float* verts, float* normals, int32_t* faces, void* stream);
+
+/* Exact nearest neighbour of every query point in a reference cloud (d = 2 or 3, row-major fp32): dist[i] = Euclidean
+ * distance, idx[i] = index of the neighbour (idx may be NULL).  Replaces KDTree(ref).query(query) of
+ * surface_reconstruction/compute_metrics_srb.py:38-42 and utils/utils.py:250-251,274-275. */
+int digs_nn_query(const float* ref, int64_t n_ref, const float* query, int64_t n_query, int d, float* dist, int32_t* idx,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif
