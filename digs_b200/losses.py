@@ -7,8 +7,10 @@ Laplacian that the drop-in DiGSNetwork.forward already produced, evaluates all l
 adjoint seeds in ONE kernel (digs_loss_fused) and hands the seeds back to the jet's reverse kernel
 when the caller runs loss.backward().
 
-In scope: loss_type in {siren, siren_wo_n, siren_w_div, siren_wo_n_w_div}, div_type in {l1, l2}.
-The curvature / ground-truth-divergence / IGR variants are outside the north-star path and raise.
+Fused path (one kernel): loss_type in {siren, siren_wo_n, siren_w_div, siren_wo_n_w_div}, div_type in {l1, l2} -- every
+recipe of the reference's run scripts.  The remaining variants (igr, igr_wo_n, *_w_curv; div_type gt_l1 / gt_l2) are
+evaluated by `_composite_terms`: the same jets from the CUDA kernels, the loss algebra as a handful of torch
+elementwise ops on them (models/losses.py:79-181), autograd carrying the seeds back into the jet's reverse kernel.
 """
 import ctypes
 
@@ -19,6 +21,7 @@ from . import _lib
 from .jet import _ptr, _stream
 
 IN_SCOPE = ("siren", "siren_wo_n", "siren_w_div", "siren_wo_n_w_div")
+COMPOSITE = ("igr", "igr_wo_n", "siren_w_curv", "siren_w_div_w_curv", "siren_wo_n_w_div_w_curv")
 _ADDS_NORMAL = ("siren", "siren_w_div")
 
 
@@ -81,15 +84,12 @@ class DiGSLoss(nn.Module):
 
     def forward(self, output_pred, mnfld_points, nonmnfld_points, mnfld_n_gt=None, nonmnfld_dist=None,
                 curvatures=None, network_weights=None, nonmnfld_div_gt=None, mnfld_div_gt=None):
-        if self.loss_type not in IN_SCOPE:
-            if any(t in self.loss_type for t in ("curv", "igr")):
-                raise NotImplementedError("digs_b200: loss_type %r is outside the fused path (models/losses.py:79-96,"
-                                          "156-160); use the reference module" % (self.loss_type,))
+        if self.loss_type not in IN_SCOPE + COMPOSITE:
             raise Warning("unrecognized loss type")
-        if self.use_div and self.div_type not in ("l1", "l2"):
-            if self.div_type in ("gt_l1", "gt_l2"):
-                raise NotImplementedError("digs_b200: div_type %r is outside the fused path" % (self.div_type,))
+        if self.use_div and self.div_type not in ("l1", "l2", "gt_l1", "gt_l2"):
             raise Warning("unsupported divergence type. only suuports l1 and l2")
+        if self.loss_type in COMPOSITE or (self.use_div and self.div_type in ("gt_l1", "gt_l2")):
+            return self._composite_terms(output_pred, mnfld_points, mnfld_n_gt, curvatures, nonmnfld_div_gt, mnfld_div_gt)
         device = mnfld_points.device
         f_n = output_pred["nonmanifold_pnts_pred"]
         f_m = output_pred["manifold_pnts_pred"]
@@ -125,6 +125,79 @@ class DiGSLoss(nn.Module):
         curv = torch.zeros((), device=device)
         return {"loss": loss, "sdf_term": det[1], "inter_term": det[2], "latent_reg_term": latent_reg_term,
                 "eikonal_term": det[3], "normals_loss": det[4], "div_loss": div_loss, "curv_loss": curv}, g_m
+
+    def _composite_terms(self, output_pred, mnfld_points, mnfld_n_gt, curvatures, nonmnfld_div_gt, mnfld_div_gt):
+        """The loss variants outside the fused kernel, on the jets the CUDA path produced (models/losses.py:79-181)."""
+        if self.global_counts is not None:
+            raise NotImplementedError("digs_b200: point-sharded means are implemented by the fused loss kernel only")
+        device = mnfld_points.device
+        f_n, f_m = output_pred["nonmanifold_pnts_pred"], output_pred["manifold_pnts_pred"]
+        g_n, g_m = output_pred.get("nonmanifold_pnts_grad"), output_pred.get("manifold_pnts_grad")
+        lap_n, lap_m = output_pred.get("nonmanifold_pnts_div"), output_pred.get("manifold_pnts_div")
+        latent_reg, latent = output_pred["latent_reg"], output_pred["latent"]
+        if f_m is None:
+            raise TypeError("DiGSLoss needs manifold predictions (models/losses.py:138)")
+        if g_n is None or g_m is None:
+            raise RuntimeError("digs_b200.DiGSLoss: output_pred carries no jet -- it must come from "
+                               "digs_b200.DiGSNetwork.forward on points with requires_grad=True")
+        zero = torch.zeros(1, device=device)
+        lo, hi = 0.1, self.div_clamp
+        curv_term, div_loss = zero, zero
+        if self.use_curvs:
+            if curvatures is None:
+                raise Warning(" loss type requires curvatuers but none were provided.")
+            if lap_m is None:
+                raise RuntimeError("digs_b200.DiGSLoss: curvature losses need DiGSNetwork.compute_manifold_laplacian = True")
+            mean_curv = curvatures.sum(dim=-1)
+            if self.div_type == "l2":
+                curv_term = (lap_m.square() - mean_curv.square()).clamp(lo, hi)
+            elif self.div_type == "l1":
+                curv_term = (lap_m.abs() - mean_curv.abs()).clamp(lo, hi)
+        if self.use_div:
+            if lap_n is None:
+                raise RuntimeError("digs_b200.DiGSLoss: divergence loss needs DiGSNetwork.compute_laplacian=True")
+            div_n = torch.where(lap_n.isnan(), torch.zeros_like(lap_n), lap_n)               # models/losses.py:107
+            if self.div_type == "l2":
+                div_term = div_n.square().clamp(lo, hi)
+            elif self.div_type == "l1":
+                div_term = div_n.abs().clamp(lo, hi)
+            else:
+                if lap_m is None:      # the reference only defines mnfld_divergence inside its curvature branch
+                    raise NameError("mnfld_divergence is undefined without a curvature loss type (models/losses.py:117-121)")
+                if self.div_type == "gt_l2":
+                    div_term = (div_n - nonmnfld_div_gt).square() + (lap_m - mnfld_div_gt).square()
+                else:
+                    div_term = (div_n.abs() - nonmnfld_div_gt.abs()).abs() + (lap_m.abs() - mnfld_div_gt.abs()).abs()
+            div_loss = div_term.mean()
+        eikonal = (torch.cat([g_n, g_m], dim=-2).norm(2, dim=2) - 1).abs().mean()             # models/losses.py:12-29
+        if mnfld_n_gt is None:
+            raise NameError("normal_term is undefined when mnfld_n_gt is None (models/losses.py:131-135,186)")
+        if "igr" in self.loss_type:
+            normal = (g_m - mnfld_n_gt).abs().norm(2, dim=1).mean()                           # norm over the POINT axis, as written
+        else:
+            normal = (1 - torch.nn.functional.cosine_similarity(g_m, mnfld_n_gt, dim=-1).abs()).mean()
+        sdf = f_m.abs().mean()
+        inter = torch.exp(-1e2 * f_n.abs()).mean()
+        w = self.weights
+        if self.loss_type in ("siren_wo_n", "igr_wo_n"):
+            w[2] = 0                                                                          # models/losses.py:153,161
+        if self.loss_type in ("igr", "igr_wo_n"):
+            w[1] = 0                                                                          # models/losses.py:156,160
+        loss = w[0] * sdf + w[3] * eikonal
+        if "igr" not in self.loss_type:
+            loss = loss + w[1] * inter
+        if self.loss_type in ("siren", "igr", "siren_w_div", "siren_w_curv", "siren_w_div_w_curv"):
+            loss = loss + w[2] * normal
+        if self.use_div:
+            loss = loss + w[4] * div_loss
+        if self.use_curvs:
+            loss = loss + w[4] * curv_term.mean()
+        latent_reg_term = latent_reg.mean() if latent_reg is not None else zero
+        if latent is not None and latent_reg is not None:
+            loss = loss + w[5] * latent_reg_term
+        return {"loss": loss, "sdf_term": sdf, "inter_term": inter, "latent_reg_term": latent_reg_term,
+                "eikonal_term": eikonal, "normals_loss": normal, "div_loss": div_loss,
+                "curv_loss": curv_term.mean()}, g_m
 
     def update_div_weight(self, current_iteration, n_iterations, params=None):
         """Piece-wise schedule for weights[4] (models/losses.py:190-228).

@@ -235,6 +235,8 @@ class DiGSNetwork(nn.Module):
                                         spatial_dim=in_dim)
         self.decoder.fc_block.precision = precision
         self.compute_laplacian = True     # the non-manifold cloud carries the Laplacian channel
+        # the curvature losses (models/losses.py:79-96) also need the Laplacian on the surface cloud
+        self.compute_manifold_laplacian = False
 
     @property
     def precision(self):
@@ -265,8 +267,10 @@ class DiGSNetwork(nn.Module):
         if mnfld_pnts is not None and self.encoder_type == "autodecoder":
             latent = non_mnfld_pnts[:, :, 3:]                          # models/DiGS.py:48
             latent_reg = latent.norm(dim=-1).mean()
+        m_lap = None
         paired = (mnfld_pnts is not None and torch.is_grad_enabled() and mnfld_pnts.requires_grad
-                  and non_mnfld_pnts.requires_grad and mnfld_pnts.is_cuda and non_mnfld_pnts.is_cuda)
+                  and non_mnfld_pnts.requires_grad and mnfld_pnts.is_cuda and non_mnfld_pnts.is_cuda
+                  and not self.compute_manifold_laplacian)
         if paired:
             # both clouds as one autograd node, their kernels overlapped on two streams (JetPairFunction)
             fc = self.decoder.fc_block
@@ -282,7 +286,7 @@ class DiGSNetwork(nn.Module):
             m_pred, m_grad = fm.reshape(bs, n_m), gm.reshape(bs, n_m, self.in_dim)
         else:
             if mnfld_pnts is not None:
-                m_pred, m_grad, _ = self._cloud(mnfld_pnts, want_lap=False)
+                m_pred, m_grad, m_lap = self._cloud(mnfld_pnts, want_lap=self.compute_manifold_laplacian)
             n_pred, n_grad, n_lap = self._cloud(non_mnfld_pnts, want_lap=self.compute_laplacian)
         return {"manifold_pnts_pred": m_pred,
                 "nonmanifold_pnts_pred": n_pred,
@@ -290,5 +294,6 @@ class DiGSNetwork(nn.Module):
                 "latent": latent,
                 # extra keys (a superset is call-compatible; the reference's callers read only the four above)
                 "manifold_pnts_grad": m_grad,
+                "manifold_pnts_div": m_lap,
                 "nonmanifold_pnts_grad": n_grad,
                 "nonmanifold_pnts_div": n_lap}

@@ -58,6 +58,67 @@ STEP_CASES = {
                          box=1.2),
 }
 
+# Loss variants outside the fused kernel (curvature / IGR / ground-truth divergence, models/losses.py:79-181): small nets,
+# extra inputs (two principal curvatures per surface point; divergence targets) drawn from the case seed.
+_SMALL3 = dict(latent_size=0, in_dim=3, decoder_hidden_dim=128, nl="sine", encoder_type="none", decoder_n_hidden_layers=2,
+               init_type="mfgi", sphere_init_params=[1.6, 0.1])
+_SMALL2 = dict(latent_size=0, in_dim=2, decoder_hidden_dim=64, nl="sine", encoder_type="none", decoder_n_hidden_layers=2,
+               init_type="siren")
+LOSSVAR_CASES = {
+    "curv_l1": dict(net=_SMALL3, loss=dict(weights=[3e3, 1e2, 1e2, 5e1, 1e2], loss_type="siren_w_curv", div_type="l1",
+                                           div_clamp=50), Nm=160, Nn=160, bs=1, seed=21, box=1.1),
+    "div_curv_l2": dict(net=_SMALL3, loss=dict(weights=[3e3, 1e2, 1e2, 5e1, 1e1], loss_type="siren_wo_n_w_div_w_curv",
+                                               div_type="l2", div_clamp=50), Nm=128, Nn=192, bs=1, seed=22, box=1.1),
+    "n_div_curv_2d": dict(net=_SMALL2, loss=dict(weights=[3e3, 1e2, 1e2, 5e1, 1e2], loss_type="siren_w_div_w_curv",
+                                                 div_type="l1", div_clamp=50), Nm=96, Nn=96, bs=2, seed=23, box=1.2),
+    "igr": dict(net=_SMALL3, loss=dict(weights=[3e3, 1e2, 1e2, 5e1, 1e2], loss_type="igr"), Nm=100, Nn=140, bs=2, seed=24,
+                box=1.1),
+    "igr_wo_n": dict(net=_SMALL3, loss=dict(weights=[3e3, 1e2, 1e2, 5e1, 1e2], loss_type="igr_wo_n"), Nm=100, Nn=100, bs=1,
+                     seed=25, box=1.1),
+    "gt_l2": dict(net=_SMALL3, loss=dict(weights=[3e3, 1e2, 1e2, 5e1, 1e0], loss_type="siren_w_div_w_curv", div_type="gt_l2",
+                                         div_clamp=50), Nm=120, Nn=120, bs=1, seed=26, box=1.1),
+    "gt_l1": dict(net=_SMALL3, loss=dict(weights=[3e3, 1e2, 1e2, 5e1, 1e0], loss_type="siren_wo_n_w_div_w_curv",
+                                         div_type="gt_l1", div_clamp=50), Nm=120, Nn=120, bs=1, seed=27, box=1.1),
+}
+
+
+def lossvar_extras(case):
+    """(curvatures (bs,Nm,2), nonmnfld_div_gt (bs,Nn), mnfld_div_gt (bs,Nm)) float32, deterministic per case."""
+    rng = np.random.RandomState(1000 + case["seed"])
+    bs, Nm, Nn = case["bs"], case["Nm"], case["Nn"]
+    curv = rng.uniform(-3.0, 3.0, size=(bs, Nm, 2)).astype(np.float32)
+    return curv, rng.uniform(-4, 4, size=(bs, Nn)).astype(np.float32), rng.uniform(-4, 4, size=(bs, Nm)).astype(np.float32)
+
+
+def run_reference_lossvar(ref_digs, case, dtype):
+    torch.manual_seed(case["seed"])
+    net = ref_digs.DiGSNetwork(**case["net"]).to(dtype)
+    crit = ref_digs.DiGSLoss(**copy.deepcopy(case["loss"]))
+    m, nrm, nm, _ = make_inputs(case, dtype)
+    curv, dgt_n, dgt_m = lossvar_extras(case)
+    m_t, n_t, nm_t = (torch.tensor(a, dtype=dtype) for a in (m, nrm, nm))
+    m_t.requires_grad_()
+    nm_t.requires_grad_()
+    out = net(nm_t, m_t)
+    loss_dict, _ = crit(out, m_t, nm_t, n_t, curvatures=torch.tensor(curv, dtype=dtype),
+                        nonmnfld_div_gt=torch.tensor(dgt_n, dtype=dtype), mnfld_div_gt=torch.tensor(dgt_m, dtype=dtype))
+    loss_dict["loss"].backward()
+    res = {"term_" + k: np.asarray(v.detach().numpy()).reshape(-1)[:1] for k, v in loss_dict.items()}
+    for name, p in net.named_parameters():
+        res["grad_" + name] = p.grad.detach().numpy().astype(np.float32)
+    res["weights_after"] = np.array(crit.weights, dtype=np.float64)
+    return res, dict(in_mnfld=m, in_normals=nrm, in_nonmnfld=nm, in_curvatures=curv, in_div_gt_n=dgt_n, in_div_gt_m=dgt_m)
+
+
+def make_lossvar(ref_digs):
+    for name, case in LOSSVAR_CASES.items():
+        r64, inputs = run_reference_lossvar(ref_digs, case, torch.float64)
+        blob = dict(inputs)
+        blob.update({"ref64_" + k: v for k, v in r64.items()})
+        np.savez_compressed(os.path.join(OUT, "lossvar_%s.npz" % name), **blob)
+        print("lossvar", name, {k[5:]: float(v[0]) for k, v in r64.items() if k.startswith("term_")})
+
+
 INIT_CASES = {
     "mfgi_c2": dict(latent_size=0, in_dim=3, decoder_hidden_dim=256, nl="sine", encoder_type="none",
                     decoder_n_hidden_layers=4, init_type="mfgi", sphere_init_params=[1.6, 0.1]),
@@ -132,6 +193,10 @@ def run_reference_step(ref_digs, case, dtype):
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref_digs, ref_losses, ref_utils = reference_loader.load()
+    if "--only-lossvar" in sys.argv:          # regenerate just the loss-variant fixtures
+        make_lossvar(ref_digs)
+        return
+    make_lossvar(ref_digs)
 
     # ---- init fingerprints -----------------------------------------------------------------------
     init = {}

@@ -16,7 +16,7 @@ from digs_b200 import _lib
 from digs_b200 import jet as djet
 from digs_b200.grid import grid_axes, grid_query, slab_range
 from oracle import jet_spec, ref_autograd
-from oracle.make_golden import STEP_CASES
+from oracle.make_golden import STEP_CASES, LOSSVAR_CASES
 from _util import golden, maxrel, build_net, np_params, head_of, param_names
 
 pytestmark = pytest.mark.gpu
@@ -82,6 +82,35 @@ def test_step_matches_reference_fixture(name, precision):
         assert maxrel(p.grad.cpu(), g["ref64_grad_" + pname]) < GRAD_TOL, pname
     if lat is not None:
         assert maxrel(lat.grad.cpu(), g["ref64_grad_latent"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x2"])
+@pytest.mark.parametrize("name", sorted(LOSSVAR_CASES))
+def test_loss_variants_match_reference_fixture(name, precision):
+    """Curvature / IGR / ground-truth-divergence losses (models/losses.py:79-181) end to end on the device: jets (incl. the
+    surface-cloud Laplacian) from the CUDA kernels, loss algebra on top, reverse kernels driven by autograd's seeds."""
+    case, g = LOSSVAR_CASES[name], golden("lossvar_%s.npz" % name)
+    if precision != "fp32" and case["net"]["decoder_hidden_dim"] % 128:
+        pytest.skip("tensor-core modes take H in {128,256,512}")
+    net = build_net(case["net"], case["seed"], precision=precision).to(DEV)
+    net.compute_manifold_laplacian = True
+    crit = digs_b200.DiGSLoss(**copy.deepcopy(case["loss"]))
+    dev = lambda k: torch.tensor(g[k], device=DEV)
+    m, nm = dev("in_mnfld").requires_grad_(), dev("in_nonmnfld").requires_grad_()
+    out = net(nm, m)
+    assert out["manifold_pnts_div"].shape == (case["bs"], case["Nm"])
+    loss_dict, _ = crit(out, m, nm, dev("in_normals"), curvatures=dev("in_curvatures"), nonmnfld_div_gt=dev("in_div_gt_n"),
+                        mnfld_div_gt=dev("in_div_gt_m"))
+    loss_dict["loss"].backward()
+    JET_TOL, GRAD_TOL = TOL[precision]
+    for key in ("loss", "sdf_term", "inter_term", "eikonal_term", "normals_loss", "div_loss", "curv_loss"):
+        ref = float(g["ref64_term_" + key][0])
+        got = float(loss_dict[key].detach().reshape(-1)[0])
+        assert abs(got - ref) <= JET_TOL * max(abs(ref), 1e-3), (key, got, ref)
+    np.testing.assert_array_equal(np.array(crit.weights, dtype=np.float64), g["ref64_weights_after"])
+    for pname, p in net.named_parameters():
+        assert p.grad is not None, pname
+        assert maxrel(p.grad.cpu(), g["ref64_grad_" + pname]) < GRAD_TOL, pname
 
 
 @pytest.mark.parametrize("precision", MODES)

@@ -1,4 +1,5 @@
 """CPU: host-side logic of the drop-in layer and the C-ABI surface (no compute calls -- there is no GPU here)."""
+import copy
 import ctypes
 import os
 import re
@@ -12,8 +13,8 @@ import torch
 import digs_b200
 from digs_b200 import _lib, dist as ddist
 from digs_b200.grid import grid_axes, slab_range
-from oracle.make_golden import INIT_CASES, INIT_SEED
-from _util import golden, sha, build_net
+from oracle.make_golden import INIT_CASES, INIT_SEED, LOSSVAR_CASES
+from _util import golden, sha, build_net, head_of, maxrel
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -101,14 +102,51 @@ def test_div_weight_schedule(decay, pname, params):
     np.testing.assert_allclose(np.array(vals), g["%s/%s" % (decay, pname)], rtol=0, atol=0)
 
 
-def test_loss_rejects_out_of_scope_modes():
-    crit = digs_b200.DiGSLoss(loss_type="siren_w_curv")
+def test_loss_rejects_unknown_modes_and_missing_inputs():
     z = torch.zeros(1, 4, 3)
-    with pytest.raises(NotImplementedError):
-        crit({"nonmanifold_pnts_pred": z, "manifold_pnts_pred": z, "latent_reg": None, "latent": None}, z, z, z)
+    pred = {"nonmanifold_pnts_pred": z, "manifold_pnts_pred": z, "latent_reg": None, "latent": None}
     with pytest.raises(Warning):
-        digs_b200.DiGSLoss(loss_type="bogus")({"nonmanifold_pnts_pred": z, "manifold_pnts_pred": z,
-                                               "latent_reg": None, "latent": None}, z, z, z)
+        digs_b200.DiGSLoss(loss_type="bogus")(pred, z, z, z)
+    with pytest.raises(Warning):
+        digs_b200.DiGSLoss(loss_type="siren_w_div", div_type="huber")(pred, z, z, z)
+    with pytest.raises(RuntimeError):                     # no jet in output_pred: it did not come from the CUDA forward
+        digs_b200.DiGSLoss(loss_type="siren_w_curv")(pred, z, z, z, curvatures=z[..., :2])
+    jets = dict(pred, nonmanifold_pnts_grad=z, manifold_pnts_grad=z)
+    with pytest.raises(Warning):                          # models/losses.py:80-81
+        digs_b200.DiGSLoss(loss_type="siren_w_curv", div_type="l1")(jets, z, z, z)
+    with pytest.raises(RuntimeError):                     # surface Laplacian was not requested from the network
+        digs_b200.DiGSLoss(loss_type="siren_w_curv", div_type="l1")(jets, z, z, z, curvatures=z[..., :2])
+
+
+@pytest.mark.parametrize("name", sorted(LOSSVAR_CASES))
+def test_composite_loss_variants_match_reference_fixture_cpu(name):
+    """The loss algebra of the curvature / IGR / gt-divergence variants (digs_b200.DiGSLoss._composite_terms) against
+    fixtures from the real reference, with the jets supplied by the autograd oracle in float64 (so only the loss
+    algebra and its gradient flow are under test here; the CUDA jets are covered by the GPU twin of this test)."""
+    from oracle import ref_autograd
+    case, g = LOSSVAR_CASES[name], golden("lossvar_%s.npz" % name)
+    net = build_net(case["net"], case["seed"]).double()
+    params = list(net.decoder.fc_block.flat_params())
+    bs, d = case["bs"], case["net"]["in_dim"]
+    m = torch.tensor(g["in_mnfld"], dtype=torch.float64).reshape(-1, d).requires_grad_()
+    nm = torch.tensor(g["in_nonmnfld"], dtype=torch.float64).reshape(-1, d).requires_grad_()
+    f_m, g_m, l_m = ref_autograd.jet(params, m, head_of(net), want_lap=True)
+    f_n, g_n, l_n = ref_autograd.jet(params, nm, head_of(net), want_lap=True)
+    pred = {"manifold_pnts_pred": f_m.reshape(bs, -1), "nonmanifold_pnts_pred": f_n.reshape(bs, -1), "latent_reg": None,
+            "latent": None, "manifold_pnts_grad": g_m.reshape(bs, -1, d), "nonmanifold_pnts_grad": g_n.reshape(bs, -1, d),
+            "manifold_pnts_div": l_m.reshape(bs, -1), "nonmanifold_pnts_div": l_n.reshape(bs, -1)}
+    crit = digs_b200.DiGSLoss(**copy.deepcopy(case["loss"]))
+    t64 = lambda k: torch.tensor(g[k], dtype=torch.float64)
+    loss_dict, mnfld_grad = crit(pred, m.reshape(bs, -1, d), nm.reshape(bs, -1, d), t64("in_normals"),
+                                 curvatures=t64("in_curvatures"), nonmnfld_div_gt=t64("in_div_gt_n"),
+                                 mnfld_div_gt=t64("in_div_gt_m"))
+    loss_dict["loss"].backward()
+    for key in ("loss", "sdf_term", "inter_term", "eikonal_term", "normals_loss", "div_loss", "curv_loss", "latent_reg_term"):
+        ref = float(g["ref64_term_" + key][0])
+        assert abs(float(loss_dict[key].reshape(-1)[0]) - ref) <= 1e-9 * max(abs(ref), 1.0), key
+    np.testing.assert_array_equal(np.array(crit.weights, dtype=np.float64), g["ref64_weights_after"])
+    for pname, p in net.named_parameters():
+        assert maxrel(p.grad, g["ref64_grad_" + pname]) < 1e-5, pname       # fixture gradients are stored in float32
 
 
 @pytest.mark.parametrize("tag", ["cube16", "box20", "zshort12"])
