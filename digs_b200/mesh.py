@@ -121,6 +121,17 @@ def sample_surface(verts, faces, count, generator=None):
     return pts, fi
 
 
+def occupancy_iou(decoder, points, occupancies):
+    """IoU of the predicted interior (SDF < 0) against ground-truth occupancies at query points: the ShapeNet metric of
+    compute_metrics_shapenet.py:131-136, evaluated with the value-only kernel and reduced on the device."""
+    pts = _as_cuda(points)
+    with torch.no_grad():
+        sdf = decoder(pts.reshape(1, -1, pts.shape[-1])).reshape(-1)
+    pred = sdf < 0
+    occ = torch.as_tensor(np.asarray(occupancies) if not torch.is_tensor(occupancies) else occupancies).to(pts.device).reshape(-1) != 0
+    return float((occ & pred).sum()) / float((occ | pred).sum())
+
+
 class TriMesh:
     """The slice of trimesh.Trimesh the reference touches: vertices / faces / vertex_normals arrays and
     `.export(path, vertex_normal=True)` (binary PLY)."""

@@ -184,3 +184,22 @@ def test_implicit2mesh_end_to_end(tmp_path):
     assert b"element vertex %d" % len(v) in head and b"element face %d" % len(f) in head and b"property float nx" in head
     assert len(body) == len(v) * 24 + len(f) * 13
     np.testing.assert_array_equal(np.frombuffer(body[:12], "<f4"), v[0])
+
+
+def test_occupancy_iou_matches_reference_formula():
+    """compute_metrics_shapenet.py:131-136: occupancy = (decoder(points) < 0); IoU = |gt & pred| / |gt | pred|."""
+    import digs_b200
+    from oracle import ref_autograd
+    from _util import head_of
+    torch.manual_seed(3627473)
+    net = digs_b200.DiGSNetwork(0, 3, 256, "sine", "none", 4, "mfgi", [1.6, 0.1]).to(DEV)
+    rng = np.random.RandomState(0)
+    pts = rng.uniform(-0.55, 0.55, size=(100000, 3)).astype(np.float32)
+    occ = (np.linalg.norm(pts, axis=1) < 0.5).astype(np.uint8)           # "ground truth": a ball a little larger than the initial sphere
+    got = digs_b200.occupancy_iou(net.decoder, pts, occ)
+    params = [p.detach().cpu() for p in net.decoder.fc_block.flat_params()]
+    ref = ref_autograd.grid_values(params, torch.tensor(pts), head_of(net)).numpy()
+    pred = (ref < 0).astype(np.uint8)
+    want = (occ & pred).sum() / (occ | pred).sum()
+    assert 0.05 < want < 1.0
+    assert abs(got - want) < 2e-4          # a handful of points within fp32 rounding of the level set may flip
