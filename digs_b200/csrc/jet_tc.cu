@@ -25,7 +25,7 @@
 // warp alternating between them); measurements chose NCTX = 1 with 128-column tiles (see Cfg).
 //
 // What the forward leaves in `saved` for the reverse pass (per cloud, n_pad = n rounded up to 8):
-//   planes   [Lh][C][n_pad][H] fp32    pre-activations scaled by 30: (30 z | 30 Z_k | 30 Q)
+//   planes   [Lh][C][n_pad/4][H][4] fp32  pre-activations scaled by 30: (30 z | 30 Z_k | 30 Q); a thread's 4 points = one float4
 //   actP     [Lh][C*n_pad][H]  uint32  layer inputs (h | A_k | P) of layers 1..Lh as (bf16 hi | bf16 lo << 16) = wgrad operand
 //   head     [n][C] fp32               (u | gu_k | lu)
 // and the reverse kernel writes GP [Lh][C*n_pad][H] uint32 = adjoints (zbar | Zbar_k | Qbar)/30, the other wgrad operand.
@@ -317,17 +317,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                 constexpr bool FULL = decltype(full_tag)::value;
                 for (int j = 0; j <= Lh; ++j) {
                     const int l = BWD ? (Lh - j) : j;          // layer whose (pre-)activations this step touches
-                    if (j > 0) {
-                        mbar_wait(acc_ready, pa);
-                        pa ^= 1;
-                        tc_fence_after();
-                    }
                     const bool last = (j == Lh);
                     const uint32_t t_buf = tmem_base + ((uint32_t)(q * 32) << 16) + (j & 1) * G::ACC_COLS;
                     // layer slot bases: planes slot = l-1 (both directions); GP slot = l-1 (reverse), actP slot = l (forward)
                     float* pl_l = a.planes ? a.planes + (int64_t)(l - 1) * C * plane_stride + p0 * H : nullptr;
                     uint32_t* wd_l = words ? words + (int64_t)(BWD ? (l - 1) : l) * C * plane_stride + p0 * H : nullptr;
 
+                    // stored pre-activations of this thread's unit for the 4-point pieces of group g (float4 each).
+                    // (Issuing the first item's loads before the accumulator wait was tried: the longer live range spilled
+                    //  ~500 B per thread and the reverse kernel lost 40 %.)
+                    auto load_planes = [&](float (&pre)[C][GP], int mt, int g) {
+                        const float* srcp = pl_l + (g * GP * H + (mt * 128 + q * 32 + lane) * 4);
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+#pragma unroll
+                            for (int h = 0; h < GP / 4; ++h) {
+                                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (FULL || p0 + g * GP + 4 * h < a.n_pad)
+                                    v = __ldg(reinterpret_cast<const float4*>(srcp + c * plane_stride + h * 4 * H));
+                                pre[c][4 * h] = v.x; pre[c][4 * h + 1] = v.y; pre[c][4 * h + 2] = v.z; pre[c][4 * h + 3] = v.w;
+                            }
+                    };
+                    if (j > 0) {
+                        mbar_wait(acc_ready, pa);
+                        pa ^= 1;
+                        tc_fence_after();
+                    }
 #pragma unroll 1
                     for (int ph = 0; ph < NPH; ++ph) {
 #pragma unroll 1
@@ -337,7 +352,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                             const int ub = mt * 4 + q;                   // 32-unit block
                             const int u = ub * 32 + lane;                // unit index
                             const int64_t pg = p0 + g * GP;              // first point of the group
-                            const int goff = g * GP * H + u;             // element offset from the tile / layer base pointers
+                            const int goff = g * GP * H + u;             // word offset from the tile / layer base ([col][unit] words)
+                            const int poff = g * GP * H + u * 4;         // plane offset ([point / 4][unit][point % 4] floats)
                             const uint32_t t_base = t_buf + mt * N;
                             float bsum = 0.f, wlsum = 0.f, w0s0 = 0.f, w0s1 = 0.f, w0s2 = 0.f;
                             float acc[C][GP];                             // TMEM values: fwd pre-activations, bwd incoming adjoint
@@ -375,14 +391,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                                 for (int c = 0; c < C; ++c)
 #pragma unroll
                                     for (int i = 0; i < GP; ++i) pre[c][i] = (c == 0) ? acc[c][i] + blv : acc[c][i];
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < C; ++c) {
-                                    const float* srcp = pl_l + c * plane_stride + goff;
-#pragma unroll
-                                    for (int i = 0; i < GP; ++i)
-                                        pre[c][i] = (FULL || pg + i < a.n_pad) ? __ldg(srcp + i * H) : 0.f;
-                                }
+                            } else if constexpr (GP % 4 == 0) {
+                                load_planes(pre, mt, g);
                             }
                             float wl_u = 0.f;
                             if ((BWD && j == 0) || (!BWD && last)) wl_u = __ldg(a.w_last + u);
@@ -455,10 +465,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                                 if (pl_l) {        // the last sine layer's pre-activations are needed by the reverse pass too
 #pragma unroll
                                     for (int c = 0; c < C; ++c) {
-                                        float* dst = pl_l + c * plane_stride + goff;
+                                        float* dst = pl_l + c * plane_stride + poff;
 #pragma unroll
-                                        for (int i = 0; i < GP; ++i)
-                                            if (FULL || pg + i < a.n_pad) dst[i * H] = pre[c][i];
+                                        for (int h = 0; h < GP / 4; ++h)
+                                            if (FULL || pg + 4 * h < a.n_pad)
+                                                *reinterpret_cast<float4*>(dst + h * 4 * H) =
+                                                    make_float4(pre[c][4 * h], pre[c][4 * h + 1], pre[c][4 * h + 2], pre[c][4 * h + 3]);
                                     }
                                 }
                             } else {
@@ -500,10 +512,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                                 if (!BWD && j > 0 && pl_l) {   // layer 0 is recomputed from the coordinates, never stored
 #pragma unroll
                                     for (int c = 0; c < C; ++c) {
-                                        float* dst = pl_l + c * plane_stride + goff;
+                                        float* dst = pl_l + c * plane_stride + poff;
 #pragma unroll
-                                        for (int i = 0; i < GP; ++i)
-                                            if (FULL || pg + i < a.n_pad) dst[i * H] = pre[c][i];
+                                        for (int h = 0; h < GP / 4; ++h)
+                                            if (FULL || pg + 4 * h < a.n_pad)
+                                                *reinterpret_cast<float4*>(dst + h * 4 * H) =
+                                                    make_float4(pre[c][4 * h], pre[c][4 * h + 1], pre[c][4 * h + 2], pre[c][4 * h + 3]);
                                     }
                                 }
                                 if (wd_l) {
