@@ -1,0 +1,99 @@
+// Pieces shared by the tcgen05 jet kernels (jet_tc.cu: one CTA per tile; jet_tc_pair.cu: CTA pairs, cta_group::2).
+#pragma once
+#include "digs_internal.h"
+#include "tc_common.cuh"
+
+namespace digs {
+namespace tcpath {
+
+using namespace digs::tc;
+
+constexpr int EPI_WARPS = 16;
+constexpr int NTHREADS = EPI_WARPS * 32 + 64;
+constexpr int STAGES = 5;
+constexpr int STAGE_BYTES = 128 * 64 * 2;  // one A tile: 128 rows x 64 k, bf16
+
+struct Args {
+    PreSrc src;               // layer-0 input (points or grid indices)
+    int64_t n, n_pad;
+    int Lh;
+    const float* w0_30;       // [H][4]: 30*W0[u][0..2], 30*b0[u]
+    const float* bias30;      // [Lh][H]: 30*b_l[u], l = 1..Lh
+    const float* w_last;      // [H]
+    const float* b_last;      // [1]
+    int head;
+    float radius, scale;
+    float* f;                 // forward outputs
+    float* grad;
+    float* lap;
+    float* planes;            // forward: written (or NULL); reverse: read
+    __nv_bfloat16* actP;      // forward: written (or NULL)
+    float* head_saved;        // forward: written (or NULL)
+    const float* ubar;        // reverse: [n][C] head adjoints (u_bar | gu_bar_k | lu_bar)
+    __nv_bfloat16* GP_words;  // reverse: written
+    float* db[DIGS_MAX_LAYERS];  // reverse: bias gradients, layers 0..Lh (accumulated)
+    float* dW0;               // reverse: (H, w0_stride), first d columns accumulated
+    int w0_stride;
+    float* dw_last;           // reverse: (H)
+    float* sb_grad;           // reverse: (n_shapes, H) or NULL
+};
+
+// sin/cos of a phase of any magnitude: two-constant Cody-Waite reduction to [-pi, pi], then MUFU
+__device__ __forceinline__ void sincos_reduced(float t, float& s, float& c) {
+    const float magic = 12582912.f;  // 1.5 * 2^23: round-to-nearest-integer trick
+    float k = fmaf(t, 0.15915494309189535f, magic) - magic;
+    float r = fmaf(k, -6.2831854820251465f, t);
+    r = fmaf(k, 1.7484556000744883e-7f, r);
+    s = __sinf(r);
+    c = __cosf(r);
+}
+
+// Sum NV (<= 32) per-lane values over the 32 lanes.  x[] is padded to P = 4, 16 or 32 entries; afterwards x[0] of
+// lane j (j < P) holds the total of value j.
+template <int P>
+__device__ __forceinline__ void warp_reduce_scatter(float* x, int lane) {
+#pragma unroll
+    for (int off = 16; off >= P; off >>= 1)
+#pragma unroll
+        for (int j = 0; j < P; ++j) x[j] += __shfl_xor_sync(0xffffffffu, x[j], off);
+#pragma unroll
+    for (int off = P / 2; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+            float send = up ? x[j] : x[j + off];
+            float keep = up ? x[j + off] : x[j];
+            x[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
+__device__ __forceinline__ void point_coords(const PreSrc& s, int64_t gp, float& x, float& y, float& z) {
+    if (s.mode == 2) {
+        int64_t g = s.grid_base + gp;
+        int iz = (int)(g % s.nz);
+        int64_t t2 = g / s.nz;
+        int ix = (int)(t2 % s.nx);
+        int iy = (int)(t2 / s.nx);
+        x = __half2float(s.ax[ix]);
+        y = __half2float(s.ay[iy]);
+        z = __half2float(s.az[iz]);
+    } else {
+        const float* xp = s.xyz + gp * s.xyz_stride;
+        x = __ldg(xp);
+        y = __ldg(xp + 1);
+        z = (s.din > 2) ? __ldg(xp + 2) : 0.f;
+    }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// paired-CTA variant of the network kernel (jet_tc_pair.cu); H = 256 only
+bool pair_supported(const DigsNet* net);
+int launch_pair(const DigsNet* net, const CUtensorMap& tmap, const Args& a, int want_jet, int want_lap, int passes, bool bwd,
+                cudaStream_t st);
+
+}  // namespace tcpath
+}  // namespace digs

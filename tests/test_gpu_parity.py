@@ -630,3 +630,21 @@ def test_device_sampler_distribution():
     assert int(s.counter[0]) == 4
     assert len(np.intersect1d(seen[0], seen[1])) < 0.3 * 15000                            # a fresh permutation every call
     assert not np.array_equal(seen[0], seen[1])
+
+
+def test_cta_pair_kernel_passes_the_same_parity_cases():
+    """The opt-in CTA-pair (cta_group::2) variant of the jet kernel (csrc/jet_tc_pair.cu, DIGS_B200_PAIR=1) must stay
+    bit-for-tolerance equivalent: the fixture, full-size and ragged-cloud cases re-run in a child process with the switch
+    set (the library reads it once per process)."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("DIGS_B200_PAIR") == "1":
+        pytest.skip("already inside the paired run")
+    env = dict(os.environ, DIGS_B200_PAIR="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-x", "-q", "-m", "gpu", "-k",
+                        "test_step_matches_reference_fixture or test_full_size_c2 or edge or grid"],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
