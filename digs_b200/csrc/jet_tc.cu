@@ -16,13 +16,14 @@
 // + jet recurrences (forward) and their adjoints (reverse) of one (unit, point) need only one thread's registers.
 //   A   bf16 hi [+ lo] tiles of 128 rows x 64 k, SWIZZLE_128B, streamed from L2 by TMA through a 5-stage mbarrier ring;
 //   B   bf16 hi [+ lo], MN-major SWIZZLE_128B, written IN PLACE by the epilogue warps as the next layer's operand:
-//       a thread owns one unit = one k row of B and stores 4 consecutive points as one 8-byte piece;
-//   D   fp32 in TMEM (H/128 tiles of N columns), read back with tcgen05.ld.32x32b.x4.
+//       a thread owns one unit = one k row of B and stores 4 (value-only: 16) consecutive points per st.shared;
+//   D   fp32 in TMEM (H/128 tiles of N columns, two buffers), read back with tcgen05.ld.32x32b.x4 / x16.
 // DIGS_MODE_BF16X2 runs three MMA passes per product (hi*hi + hi*lo + lo*hi); DIGS_MODE_BF16 runs hi*hi only.
 // Layer 0 (K = d) and the last layer (N = 1) are fp32 FMAs / warp reductions from registers.
 //
-// The kernel is written for NCTX tile contexts per CTA (own operand buffer, TMEM columns and epilogue warps, the MMA
-// warp alternating between them); measurements chose NCTX = 1 with 128-column tiles (see Cfg).
+// A layer step runs in two operand phases (Cfg::NPH): the epilogue first finishes the units of the lower half of the next
+// layer's K range and releases them (b_ready[0]), so the MMA warp starts the next layer on those K slabs -- into the
+// other TMEM accumulator buffer -- while the epilogue is still producing the upper half (b_ready[1]).
 //
 // What the forward leaves in `saved` for the reverse pass (per cloud, n_pad = n rounded up to 8):
 //   planes   [Lh][C][n_pad/4][H][4] fp32  pre-activations scaled by 30: (30 z | 30 Z_k | 30 Q); a thread's 4 points = one float4
