@@ -78,7 +78,8 @@ struct Cfg {
     static constexpr int OFF_HEAD = OFF_XYZ + N * 3 * 4;                  // [NUB][N] floats
     static constexpr int OFF_UBAR = OFF_HEAD + NUB * N * 4;               // [N] floats
     static constexpr int OFF_BAR = OFF_UBAR + N * 4;
-    static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;               // + alignment slack
+    static constexpr int OFF_ACC = OFF_BAR + 256;                         // reverse: [(Lh+1) db | 3 dW0 | dw_last][H] floats (optional)
+    static constexpr int SMEM_BYTES = OFF_ACC + 1024;                     // + alignment slack (without the accumulators)
     static_assert(H == 128 || H == 256 || H == 512, "H must be 128, 256 or 512");
     static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(NITEMS >= WQ, "every epilogue warp needs at least one item per phase (it arrives on b_ready after its last)");
@@ -112,6 +113,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
     }
     if (warp == EPI_WARPS + 1) tmem_alloc<G::TMEM_COLS>(tmem_slot);
     for (int i = tid; i < G::OFF_RING / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    // Reverse pass: per-unit gradients (biases, layer 0, last layer) are summed per CTA in shared memory over all its
+    // tiles and flushed once at the end -- one global atomic per (CTA, unit, tensor) instead of one per (item, unit):
+    // the per-item global atomics all hit the same few hundred addresses and cost 67 us of a 300 us kernel.
+    float* sAcc = reinterpret_cast<float*>(smem + G::OFF_ACC);
+    const int n_acc = (BWD && a.acc_smem) ? (a.Lh + 5) * H : 0;
+    for (int i = tid; i < n_acc; i += NTHREADS) sAcc[i] = 0.f;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -457,14 +464,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                             }
                             // ---------------- per-unit parameter gradients of this item ---------------------------------
                             if (BWD) {
-                                if (j == 0) atomicAdd(a.dw_last + u, wlsum);
-                                if (l >= 1) {
-                                    atomicAdd(a.db[l] + u, 30.f * bsum);
+                                if (n_acc) {
+                                    if (j == 0) atomicAdd(sAcc + (Lh + 4) * H + u, wlsum);
+                                    if (l >= 1 || !a.sb_grad) atomicAdd(sAcc + l * H + u, 30.f * bsum);
+                                    if (l == 0) {
+                                        if constexpr (D > 0) atomicAdd(sAcc + (Lh + 1) * H + u, 30.f * w0s0);
+                                        if constexpr (D > 1) atomicAdd(sAcc + (Lh + 2) * H + u, 30.f * w0s1);
+                                        if constexpr (D > 2) atomicAdd(sAcc + (Lh + 3) * H + u, 30.f * w0s2);
+                                    }
                                 } else {
-                                    if (!a.sb_grad) atomicAdd(a.db[0] + u, 30.f * bsum);
-                                    if constexpr (D > 0) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 0, 30.f * w0s0);
-                                    if constexpr (D > 1) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 1, 30.f * w0s1);
-                                    if constexpr (D > 2) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 2, 30.f * w0s2);
+                                    if (j == 0) atomicAdd(a.dw_last + u, wlsum);
+                                    if (l >= 1) {
+                                        atomicAdd(a.db[l] + u, 30.f * bsum);
+                                    } else {
+                                        if (!a.sb_grad) atomicAdd(a.db[0] + u, 30.f * bsum);
+                                        if constexpr (D > 0) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 0, 30.f * w0s0);
+                                        if constexpr (D > 1) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 1, 30.f * w0s1);
+                                        if constexpr (D > 2) atomicAdd(a.dW0 + (int64_t)u * a.w0_stride + 2, 30.f * w0s2);
+                                    }
                                 }
                             }
                         }
@@ -523,6 +540,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                 }
             }
             named_bar_sync(1, G::ETHREADS);   // sXyz / sHead / sUbar are rewritten by the next tile
+        }
+        if (n_acc) {
+            // every epilogue warp has passed the barrier above for its last tile: the CTA's sums are complete
+            for (int i = tid; i < n_acc; i += G::ETHREADS) {
+                const float v = sAcc[i];
+                const int row = i / H, uu = i % H;
+                if (row <= Lh) {
+                    if (row >= 1 || !a.sb_grad) atomicAdd(a.db[row] + uu, v);
+                } else if (row <= Lh + 3) {
+                    if (row - (Lh + 1) < D) atomicAdd(a.dW0 + (int64_t)uu * a.w0_stride + (row - (Lh + 1)), v);
+                } else {
+                    atomicAdd(a.dw_last + uu, v);
+                }
+            }
         }
     }
     tc_fence_before();
@@ -617,13 +648,20 @@ static int launch(const CUtensorMap& tmap, const Args& a, cudaStream_t st) {
     auto kern = k_tc_net<D, LAP, H, PASSES, BWD>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("tc net: smem attribute (%d B): %s", G::SMEM_BYTES, cudaGetErrorString(e)); return DIGS_ECUDA; }
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) { set_error("tc net: smem attribute: %s", cudaGetErrorString(e)); return DIGS_ECUDA; }
         attr_set = true;
+    }
+    Args aa = a;
+    int smem_bytes = G::SMEM_BYTES;
+    if (BWD) {      // shared-memory gradient accumulators when they fit next to the operand buffer and the weight ring
+        const int acc_bytes = (a.Lh + 5) * H * 4;
+        aa.acc_smem = (G::SMEM_BYTES + acc_bytes <= 232448) ? 1 : 0;
+        if (aa.acc_smem) smem_bytes += acc_bytes;
     }
     int64_t tiles = (a.n_pad + G::T - 1) / G::T;
     int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    kern<<<grid, NTHREADS, G::SMEM_BYTES, st>>>(tmap, a);
+    kern<<<grid, NTHREADS, smem_bytes, st>>>(tmap, aa);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("tc net launch: %s", cudaGetErrorString(e)); return DIGS_ECUDA; }

@@ -36,6 +36,7 @@ struct Args {
     int w0_stride;
     float* dw_last;           // reverse: (H)
     float* sb_grad;           // reverse: (n_shapes, H) or NULL
+    int acc_smem;             // reverse: per-CTA shared-memory accumulators for the per-unit gradients (they fit)
 };
 
 // sin/cos of a phase of any magnitude: two-constant Cody-Waite reduction to [-pi, pi], then MUFU
