@@ -301,6 +301,19 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         ms_grid = e0.elapsed_time(e1)
         grid_pts = len(axes[0]) * ny * len(axes[2])
+        # mesh extraction from this rank's slab (utils/utils.py:354: marching cubes on the host in the reference), one pass
+        mesh_info = None
+        if rank == 0:
+            from digs_b200 import mesh as dmesh
+            dmesh.marching_tets(out_vol[:8].contiguous(), 0.0)                # warm-up
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            mv, mf, _ = dmesh.marching_tets(out_vol, 0.0, axis_of=(1, 0, 2))
+            m1.record()
+            torch.cuda.synchronize(dev)
+            mesh_info = {"ms": m0.elapsed_time(m1), "vertices": int(mv.shape[0]), "faces": int(mf.shape[0]),
+                         "what": "marching tetrahedra on rank 0's slab of the volume (3 kernels + 2 prefix sums)"}
+            del mv, mf
 
     t = torch.tensor([ms_dev, ms_e2e, ms_grid], dtype=torch.float64, device=dev)
     if world > 1:
@@ -337,6 +350,8 @@ def run_ours(args, rank, world, local_rank):
                                   "ms": ms_grid, "output": "fp32 volume resident in HBM",
                                   "roofline": {"bound": "tensor", "achieved": gt, "peak": peaks["sustained"], "unit": "TFLOP/s",
                                                "frac": gt / peaks["sustained"], "algorithmic_mflop_per_query": flop_pt / 1e6}}
+            if mesh_info is not None:
+                line["grid_query"]["mesh_extraction"] = mesh_info
         if world == 1 and not args.no_cpu:
             v, ms, cores, sample = cpu_reference_steps(3, 1)
             line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample,

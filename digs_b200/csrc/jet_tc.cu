@@ -75,11 +75,11 @@ struct Cfg {
     static constexpr int NUB = H / 32;                // 32-unit blocks
     static constexpr int OFF_RING = B_BYTES;
     static constexpr int OFF_XYZ = OFF_RING + STAGES * STAGE_BYTES;      // [N*3] floats
-    static constexpr int OFF_HEAD = OFF_XYZ + N * 3 * 4;                  // [NUB][N] floats
-    static constexpr int OFF_UBAR = OFF_HEAD + NUB * N * 4;               // [N] floats
+    static constexpr int OFF_UBAR = OFF_XYZ + N * 3 * 4;                  // [N] floats
     static constexpr int OFF_BAR = OFF_UBAR + N * 4;
-    static constexpr int OFF_ACC = OFF_BAR + 256;                         // reverse: [(Lh+1) db | 3 dW0 | dw_last][H] floats (optional)
-    static constexpr int SMEM_BYTES = OFF_ACC + 1024;                     // + alignment slack (without the accumulators)
+    static constexpr int OFF_HEAD = OFF_BAR + 256;                        // forward: [NUB][N] floats of last-layer partial sums
+    static constexpr int OFF_ACC = OFF_HEAD;                              // reverse: [(Lh+1) db | 3 dW0 | dw_last][H] floats (optional)
+    static constexpr int SMEM_BYTES = OFF_HEAD + NUB * N * 4 + 1024;      // + alignment slack; the reverse kernel adds the accumulators
     static_assert(H == 128 || H == 256 || H == 512, "H must be 128, 256 or 512");
     static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(NITEMS >= WQ, "every epilogue warp needs at least one item per phase (it arrives on b_ready after its last)");
@@ -656,8 +656,9 @@ static int launch(const CUtensorMap& tmap, const Args& a, cudaStream_t st) {
     int smem_bytes = G::SMEM_BYTES;
     if (BWD) {      // shared-memory gradient accumulators when they fit next to the operand buffer and the weight ring
         const int acc_bytes = (a.Lh + 5) * H * 4;
-        aa.acc_smem = (G::SMEM_BYTES + acc_bytes <= 232448) ? 1 : 0;
-        if (aa.acc_smem) smem_bytes += acc_bytes;
+        const int with_acc = G::OFF_ACC + acc_bytes + 1024;    // the accumulators take the place of the forward's head scratch
+        aa.acc_smem = (with_acc <= 232448) ? 1 : 0;
+        if (aa.acc_smem && with_acc > smem_bytes) smem_bytes = with_acc;
     }
     int64_t tiles = (a.n_pad + G::T - 1) / G::T;
     int grid = (int)(tiles < num_sms() ? tiles : num_sms());
