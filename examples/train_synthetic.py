@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--graph", action="store_true", help="GraphedStep + FusedClipAdam instead of eager autograd + torch Adam")
     ap.add_argument("--device-sampler", action="store_true", help="with --graph: draw every batch on the device, inside the graph")
     ap.add_argument("--grid_res", type=int, default=128)
+    ap.add_argument("--ply", default="", help="write the extracted mesh to this .ply file")
     args = ap.parse_args()
     dev = torch.device("cuda")
     torch.manual_seed(0)
@@ -69,6 +70,16 @@ def main():
     inside = float((vol < 0).float().mean())
     print("grid %d^3: SDF in [%.3f, %.3f], %.1f %% of the box inside the surface" % (args.grid_res, float(vol.min()),
                                                                                    float(vol.max()), 100 * inside))
+    # test-time path of the reference (test_surface_reconstruction.py:59-61, compute_metrics_srb.py:38-57,75), all on the device
+    t1 = time.time()
+    mesh = DiGSNet.implicit2mesh(net.decoder, None, args.grid_res, device=dev)["mesh_obj"]
+    recon, _ = mesh.sample_surface(min(1000000, 20 * len(cloud)))
+    cd, hd, cd_re2gt, cd_gt2re, _, _ = DiGSNet.compute_dists(recon, cloud)
+    torch.cuda.synchronize()
+    print("mesh: %d vertices, %d faces; Chamfer to the input cloud %.5f (recon->gt %.5f, gt->recon %.5f), Hausdorff %.4f  [%.2f s]"
+          % (len(mesh.vertices), len(mesh.faces), cd, cd_gt2re, cd_re2gt, hd, time.time() - t1))
+    if args.ply:
+        mesh.export(args.ply, vertex_normal=True)
 
 
 if __name__ == "__main__":
