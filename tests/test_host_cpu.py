@@ -46,6 +46,17 @@ def test_library_rejects_bad_arguments_without_a_gpu():
     # tensor-core modes are explicit: never a silent fallback
     assert L.digs_saved_bytes(ctypes.byref(net), 10, 1, 7) == 0
     assert L.digs_saved_bytes(ctypes.byref(net), 1000, 1, 0) >= 4 * 5 * 1000 * 256 * 4
+    # mesh / nearest-neighbour entry points validate before touching the device
+    assert L.digs_mt_classify(None, 8, 8, 8, 0.0, None, None, None) == -1
+    assert b"NULL" in L.digs_last_error()
+    assert L.digs_mt_classify(256, 1, 8, 8, 0.0, 256, 256, None) == -1            # a volume needs 2 points per axis
+    ax = (ctypes.c_int * 3)(0, 0, 2)
+    f3 = (ctypes.c_float * 3)(1.0, 1.0, 1.0)
+    assert L.digs_mt_emit(256, 8, 8, 8, 0.0, ax, f3, f3, 256, 256, 256, 256, 256, None, 256, None) == -1
+    assert b"permutation" in L.digs_last_error()
+    assert L.digs_nn_query(256, 10, 256, 10, 4, 256, None, None) == -1             # d must be 2 or 3
+    assert L.digs_nn_query(256, 0, 256, 10, 3, 256, None, None) == -1              # empty reference cloud
+    assert L.digs_nn_query(None, 10, None, 0, 3, None, None, None) == 0            # nothing to query
 
 
 @pytest.mark.parametrize("name", sorted(INIT_CASES))
