@@ -40,6 +40,7 @@ FLOP_STEP = 3 * N_POINTS * (FLOP_FWD_NONMNFLD + FLOP_FWD_MNFLD)
 # per launch, from the `ncu --set full` capture summarised in profiles/r01_full_tc_kernels.md.  The kernel's algorithmic
 # bytes are the saved planes + wgrad operand: 2 * 15000 * 4 layers * 5 channels * 256 units * 4 B = 614 MB.
 FWD_DRAM_BYTES = {"bf16x2": 559.65e6}
+FWD_SAVED_BYTES = N_POINTS * (LH * 5 * H * 8 + 5 * 4)      # C = 5 channels: fp32 planes + (hi|lo) words per layer, head per point
 
 
 def measured_peaks():
@@ -283,6 +284,16 @@ def run_ours(args, rank, world, local_rank):
         kev.append((e0, e1))
     torch.cuda.synchronize()
     ms_fwd = sum(a.elapsed_time(b) for a, b in kev) / reps
+    # pure-write bandwidth of this part, measured on the 256 MiB flush fill: the saving kernels write far more than they read
+    fev = []
+    for r in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        flush.fill_(r)
+        e1.record()
+        fev.append((e0, e1))
+    torch.cuda.synchronize()
+    fill_gbs = flush.numel() / (min(a.elapsed_time(b) for a, b in fev) * 1e-3) / 1e9
 
     # ---- second half of the metric: MC grid queries/s, grid_res^3 points sharded by iy slab over the ranks -----
     ms_grid, grid_pts = 0.0, 0
@@ -338,6 +349,13 @@ def run_ours(args, rank, world, local_rank):
                              "kernel": "forward jet of the 15000-point off-surface cloud (C=5 channels), timed alone",
                              "ms": ms_fwd, "algorithmic_gflop": N_POINTS * FLOP_FWD_NONMNFLD / 1e9,
                              "peak_source": peaks["source"] + " bf16 dense burst",
+                             "hbm_view": {"what": "the same kernel as an HBM problem: it writes the state the reverse pass needs "
+                                                  "(planes + layer-input words + head: Lh*C*H*8 + C*4 bytes per point)",
+                                          "algorithmic_bytes": FWD_SAVED_BYTES, "achieved": FWD_SAVED_BYTES / (ms_fwd * 1e-3) / 1e9,
+                                          "peak": peaks["hbm"], "unit": "GB/s",
+                                          "frac": FWD_SAVED_BYTES / (ms_fwd * 1e-3) / 1e9 / peaks["hbm"],
+                                          "fill_GBps_measured": fill_gbs,
+                                          "frac_of_fill": FWD_SAVED_BYTES / (ms_fwd * 1e-3) / 1e9 / fill_gbs},
                              "whole_step": {"achieved": step_tflops, "peak": peaks["sustained"],
                                             "frac": step_tflops / peaks["sustained"],
                                             "algorithmic_gflop": FLOP_STEP / 1e9,
