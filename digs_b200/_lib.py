@@ -26,6 +26,20 @@ class DigsNet(ctypes.Structure):
         ("reserved", ctypes.c_int32),
         ("W", ctypes.c_void_p * MAX_LAYERS),
         ("b", ctypes.c_void_p * MAX_LAYERS),
+        ("prepared", ctypes.c_void_p),
+    ]
+
+
+class DigsLossCfg(ctypes.Structure):
+    _fields_ = [
+        ("weights", ctypes.c_float * 6),
+        ("weights_device", ctypes.c_void_p),
+        ("add_normal", ctypes.c_int32),
+        ("use_div", ctypes.c_int32),
+        ("div_l2", ctypes.c_int32),
+        ("div_clamp", ctypes.c_float),
+        ("Nm_total", ctypes.c_int64),
+        ("Nn_total", ctypes.c_int64),
     ]
 
 
@@ -39,7 +53,9 @@ class DigsGrads(ctypes.Structure):
 EXPORTS = (
     "digs_abi_version", "digs_last_error", "digs_launch_count", "digs_saved_bytes", "digs_forward_workspace_bytes",
     "digs_backward_workspace_bytes", "digs_value_workspace_bytes", "digs_grid_workspace_bytes",
-    "digs_jet_forward", "digs_jet_backward", "digs_loss_fused", "digs_loss_fused_dw", "digs_value_forward", "digs_grid_query", "digs_clip_adam", "digs_sample_batch",
+    "digs_prepared_bytes", "digs_prepare_weights", "digs_step_workspace_bytes", "digs_step_fused",
+    "digs_jet_forward", "digs_jet_backward", "digs_loss_fused", "digs_loss_fused_dw", "digs_value_forward", "digs_grid_query",
+    "digs_clip_adam", "digs_clip_adam_dev", "digs_sample_batch",
     "digs_mt_classify", "digs_mt_emit", "digs_nn_query",
 )
 
@@ -89,6 +105,18 @@ def lib():
     L.digs_clip_adam.restype = i32
     L.digs_clip_adam.argtypes = [vp, vp, vp, vp, i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                  ctypes.c_float, i32, vp, vp]
+    L.digs_clip_adam_dev.restype = i32
+    L.digs_clip_adam_dev.argtypes = [vp, vp, vp, vp, i64, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                     ctypes.c_float, vp, vp, vp]
+    L.digs_prepared_bytes.restype = sz
+    L.digs_prepared_bytes.argtypes = [netp, i32]
+    L.digs_prepare_weights.restype = i32
+    L.digs_prepare_weights.argtypes = [netp, vp, sz, i32, vp]
+    L.digs_step_workspace_bytes.restype = sz
+    L.digs_step_workspace_bytes.argtypes = [netp, i64, i64, i32, i32]
+    L.digs_step_fused.restype = i32
+    L.digs_step_fused.argtypes = [netp, vp, i64, vp, i64, vp, i64, vp, vp, i64, i64, i32, ctypes.POINTER(DigsLossCfg),
+                                  vp, vp, vp, vp, vp, vp, ctypes.POINTER(DigsGrads), vp, vp, vp, sz, i32, vp]
     L.digs_sample_batch.restype = i32
     L.digs_sample_batch.argtypes = [vp, vp, i64, i32, i64, ctypes.c_float, ctypes.c_uint64, vp, vp, vp, vp, vp]
     L.digs_mt_classify.restype = i32
@@ -98,7 +126,7 @@ def lib():
                                ctypes.POINTER(ctypes.c_float), vp, vp, vp, vp, vp, vp, vp, vp]
     L.digs_nn_query.restype = i32
     L.digs_nn_query.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp]
-    if L.digs_abi_version() != 1:
+    if L.digs_abi_version() != 2:
         raise RuntimeError("digs_b200: ABI version mismatch")
     _lib = L
     return L

@@ -102,6 +102,54 @@ size_t digs_grid_workspace_bytes(const DigsNet* net, int mode) {
     return simt::grid_ws_bytes(net);
 }
 
+size_t digs_prepared_bytes(const DigsNet* net, int mode) {
+    if (check_net(net) || check_mode(net, mode)) return 0;
+    return is_tc(mode) ? tcpath::prep_ws_bytes(net) : 0;
+}
+int digs_prepare_weights(const DigsNet* net, void* prepared, size_t prepared_bytes, int mode, void* stream) {
+    int rc;
+    if ((rc = check_net(net)) || (rc = check_mode(net, mode))) return rc;
+    if (!is_tc(mode)) return DIGS_OK;
+    if (!prepared || prepared_bytes < tcpath::prep_ws_bytes(net)) { set_error("prepare_weights: buffer too small"); return DIGS_ENOSPACE; }
+    return tcpath::run_prep(net, prepared, (cudaStream_t)stream);
+}
+
+size_t digs_step_workspace_bytes(const DigsNet* net, int64_t nn, int64_t nm, int want_lap, int mode) {
+    if (check_net(net) || check_mode(net, mode) || nn < 0 || nm < 0 || !is_tc(mode)) return 0;
+    return tcpath::step_ws_bytes(net, nn, nm, want_lap);
+}
+int digs_step_fused(const DigsNet* net, const float* nonmnfld, int64_t nn, const float* mnfld, int64_t nm,
+                    const float* normals, int64_t xyz_stride, const float* shape_bias_n, const float* shape_bias_m,
+                    int64_t pts_per_shape_n, int64_t pts_per_shape_m, int want_lap, const DigsLossCfg* cfg, float* f_n,
+                    float* g_n, float* lap_n, float* f_m, float* g_m, float* terms_out, const DigsGrads* grads,
+                    float* sb_grad_n, float* sb_grad_m, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+    int rc;
+    if ((rc = check_net(net)) || (rc = check_mode(net, mode))) return rc;
+    if (!is_tc(mode)) { set_error("step_fused: tensor-core modes only (use the two-call API in fp32 mode)"); return DIGS_ENOTIMPL; }
+    if (nn < 0 || nm < 0 || xyz_stride < net->d) { set_error("step_fused: bad counts / xyz_stride"); return DIGS_EINVAL; }
+    if (nn + nm == 0) return DIGS_OK;
+    if (!cfg || !terms_out || !grads) { set_error("step_fused: NULL cfg / terms / grads"); return DIGS_EINVAL; }
+    if (nn > 0 && (!nonmnfld || !f_n || !g_n)) { set_error("step_fused: NULL off-surface buffer"); return DIGS_EINVAL; }
+    if (nm > 0 && (!mnfld || !f_m || !g_m)) { set_error("step_fused: NULL surface buffer"); return DIGS_EINVAL; }
+    if (cfg->use_div && !want_lap) { set_error("step_fused: divergence loss needs want_lap"); return DIGS_EINVAL; }
+    if (cfg->add_normal && !normals) { set_error("step_fused: normal term without normals"); return DIGS_EINVAL; }
+    for (int l = 0; l <= net->Lh + 1; ++l)
+        if (!grads->dW[l] || !grads->db[l]) { set_error("step_fused: grads.dW[%d]/db[%d] NULL", l, l); return DIGS_EINVAL; }
+    if ((shape_bias_n && (!sb_grad_n || pts_per_shape_n <= 0)) || (shape_bias_m && (!sb_grad_m || pts_per_shape_m <= 0)) ||
+        ((shape_bias_n != nullptr) != (shape_bias_m != nullptr) && nn > 0 && nm > 0)) {
+        set_error("step_fused: shape_bias needs shape_bias_grad and pts_per_shape on both clouds");
+        return DIGS_EINVAL;
+    }
+    size_t need = digs_step_workspace_bytes(net, nn, nm, want_lap, mode);
+    if (!workspace || workspace_bytes < need) {
+        set_error("step_fused: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return DIGS_ENOSPACE;
+    }
+    return tcpath::step_fused(net, nonmnfld, nn, mnfld, nm, normals, xyz_stride, shape_bias_n, shape_bias_m, pts_per_shape_n,
+                              pts_per_shape_m, want_lap, cfg, f_n, g_n, lap_n, f_m, g_m, terms_out, grads, sb_grad_n,
+                              sb_grad_m, workspace, passes_of(mode), (cudaStream_t)stream);
+}
+
 int digs_jet_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_stride, const float* shape_bias,
                      int64_t pts_per_shape, int want_lap, float* f, float* grad, float* lap, void* saved,
                      size_t saved_bytes, void* workspace, size_t workspace_bytes, int mode, void* stream) {
@@ -287,7 +335,16 @@ int digs_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_s
         set_error("clip_adam: NULL buffer");
         return DIGS_EINVAL;
     }
-    return clip_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, max_norm, step, scratch,
+    return clip_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, max_norm, step, nullptr, scratch,
+                     (cudaStream_t)stream);
+}
+
+int digs_clip_adam_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float max_norm, int32_t* step_counter, float* scratch, void* stream) {
+    if (n < 0 || !step_counter) { set_error("clip_adam_dev: bad n / NULL step counter"); return DIGS_EINVAL; }
+    if (n == 0) return DIGS_OK;
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !scratch) { set_error("clip_adam_dev: NULL buffer"); return DIGS_EINVAL; }
+    return clip_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, max_norm, 0, step_counter, scratch,
                      (cudaStream_t)stream);
 }
 

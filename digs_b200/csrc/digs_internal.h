@@ -82,6 +82,12 @@ int forward(const DigsNet* net, const PreSrc& src, int64_t n, int want_jet, int 
 int backward(const DigsNet* net, const PreSrc& src, int64_t n, int want_lap, const float* f_bar, const float* g_bar,
              const float* l_bar, const void* saved, void* ws, const DigsGrads* grads, float* sb_grad, int passes,
              cudaStream_t st);
+size_t step_ws_bytes(const DigsNet* net, int64_t nn, int64_t nm, int want_lap);
+int run_prep(const DigsNet* net, void* dst, cudaStream_t st);
+int step_fused(const DigsNet* net, const float* nonmnfld, int64_t nn, const float* mnfld, int64_t nm, const float* normals,
+               int64_t xyz_stride, const float* sb_n, const float* sb_m, int64_t pps_n, int64_t pps_m, int want_lap,
+               const DigsLossCfg* cfg, float* f_n, float* g_n, float* lap_n, float* f_m, float* g_m, float* terms,
+               const DigsGrads* grads, float* sbg_n, float* sbg_m, void* ws, int passes, cudaStream_t st);
 int wgrad(const DigsNet* net, const __nv_bfloat16* GP_words, const __nv_bfloat16* actP, int C, int64_t n_pad,
           const DigsGrads* grads, int passes, cudaStream_t st);
 }  // namespace tcpath
@@ -99,7 +105,7 @@ int sample_batch(const float* cloud, const float* normals, int64_t n_cloud, int 
 
 // ---- optimizer tail (optim.cu) ------------------------------------------------------------------
 int clip_adam(float* p, float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float max_norm,
-              int step, float* scratch, cudaStream_t st);
+              int step, int32_t* step_dev, float* scratch, cudaStream_t st);
 
 // ---- iso-surface extraction and nearest neighbours (mesh.cu) ------------------------------------
 namespace mesh {

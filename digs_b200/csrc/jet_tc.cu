@@ -41,51 +41,6 @@
 namespace digs {
 namespace tcpath {
 
-template <int D, int LAP, int H_, int PASSES>
-struct Cfg {
-    static constexpr int C = 1 + D + LAP;
-    static constexpr int H = H_;
-    // One tile context per CTA.  (Two 64-column contexts ping-ponging on the MMA warp were measured SLOWER: a
-    // tcgen05.mma with N = 64 re-reads the 4 KB A tile from shared memory for half the math, and the operand fetch,
-    // not the tensor pipe, becomes the limit.)
-    static constexpr int N = (H_ > 256) ? 64 : 128;   // UMMA N = operand columns per tile (64 keeps X in smem at H=512)
-    static constexpr int GP = (C == 1) ? 16 : 4;      // points per epilogue group (one tcgen05.ld per channel)
-    static constexpr int T = (N / C) / GP * GP;       // points per tile (whole groups)
-    static constexpr int NGRP = T / GP;
-    static constexpr int MT = H / 128;                // UMMA M tiles
-    // Operand phases: the epilogue finishes the units of the first MT/2 M tiles (= the first half of the next layer's K
-    // range) before it touches the rest, so the MMA warp starts the next layer on those K slabs while the epilogue
-    // is still working on the second half.  Accumulators are double-buffered in TMEM for that.
-    static constexpr int NPH = (MT >= 2) ? 2 : 1;
-    static constexpr int MTP = MT / NPH;              // M tiles per phase
-    static constexpr int WQ = EPI_WARPS / 4;          // epilogue warps per TMEM lane quarter
-    static constexpr int NITEMS = MTP * NGRP;         // (M tile, point group) work items per quarter and phase
-    static constexpr int ROT = WQ / 2;                // item rotation between phases (balances 6 items over 4 warps)
-    static constexpr int NG = N / 64;                 // 64-column groups of the MN-major operand
-    static constexpr int SN = 1024;                   // byte stride between column groups   (descriptor LBO)
-    static constexpr int SK = NG * 1024;              // byte stride between 8-deep k groups (descriptor SBO)
-    static constexpr int B_PART = (H / 8) * SK;       // bytes of one operand part (hi or lo)
-    static constexpr int NPARTS = (PASSES == 3) ? 2 : 1;
-    static constexpr int B_BYTES = B_PART * NPARTS;
-    static constexpr int KSLABS = H / 64;
-    static constexpr int KS_PER_PH = KSLABS / NPH;
-    static constexpr int ACC_COLS = MT * N;           // TMEM columns of one accumulator buffer
-    static constexpr int TMEM_COLS = (2 * ACC_COLS <= 256) ? 256 : 512;
-    static constexpr int ETHREADS = EPI_WARPS * 32;
-    static constexpr int NUB = H / 32;                // 32-unit blocks
-    static constexpr int OFF_RING = B_BYTES;
-    static constexpr int OFF_XYZ = OFF_RING + STAGES * STAGE_BYTES;      // [N*3] floats
-    static constexpr int OFF_UBAR = OFF_XYZ + N * 3 * 4;                  // [N] floats
-    static constexpr int OFF_BAR = OFF_UBAR + N * 4;
-    static constexpr int OFF_HEAD = OFF_BAR + 256;                        // forward: [NUB][N] floats of last-layer partial sums
-    static constexpr int OFF_ACC = OFF_HEAD;                              // reverse: [(Lh+1) db | 3 dW0 | dw_last][H] floats (optional)
-    static constexpr int SMEM_BYTES = OFF_HEAD + NUB * N * 4 + 1024;      // + alignment slack; the reverse kernel adds the accumulators
-    static_assert(H == 128 || H == 256 || H == 512, "H must be 128, 256 or 512");
-    static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
-    static_assert(NITEMS >= WQ, "every epilogue warp needs at least one item per phase (it arrives on b_ready after its last)");
-    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-};
-
 template <int D, int LAP, int H, int PASSES, bool BWD>
 __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ CUtensorMap tmapW, Args a) {
     using G = Cfg<D, LAP, H, PASSES>;
@@ -632,25 +587,26 @@ size_t bwd_ws_bytes(const DigsNet* net, int64_t n, int want_lap) {
     return prep_ws_bytes(net) + s.act_bytes /* GP_words */ + s.head_bytes /* ubar */;
 }
 
-int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return n;
+int num_sms() {      // of the CURRENT device (cached per device ordinal)
+    static int n[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& slot = n[dev & 63];
+    if (!slot) cudaDeviceGetAttribute(&slot, cudaDevAttrMultiProcessorCount, dev);
+    return slot;
 }
 
 template <int D, int LAP, int H, int PASSES, bool BWD>
 static int launch(const CUtensorMap& tmap, const Args& a, cudaStream_t st) {
     using G = Cfg<D, LAP, H, PASSES>;
     auto kern = k_tc_net<D, LAP, H, PASSES, BWD>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};      // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) { set_error("tc net: smem attribute: %s", cudaGetErrorString(e)); return DIGS_ECUDA; }
-        attr_set = true;
+        attr_set[dev & 63] = true;
     }
     Args aa = a;
     int smem_bytes = G::SMEM_BYTES;
@@ -680,8 +636,9 @@ static int launch_h(const DigsNet* net, const CUtensorMap& tmap, const Args& a, 
     return DIGS_ENOTIMPL;
 }
 
-// The CTA-pair kernel (jet_tc_pair.cu, H = 256) is correct but measured slower than this file's kernel on the B200; it
-// runs only when DIGS_B200_PAIR=1 is set in the environment (A/B measurements, parity test).
+// The CTA-pair kernel (jet_tc_pair.cu, H = 256) is correct but measured slower than this file's kernel on the B200.  It is
+// NOT part of the default build: `make PAIR=1` compiles it in, and it then runs only when DIGS_B200_PAIR=1 is set.
+#ifdef DIGS_WITH_PAIR
 static bool use_pair(const DigsNet* net) {
     static int pair = -1;
     if (pair < 0) {
@@ -690,11 +647,14 @@ static bool use_pair(const DigsNet* net) {
     }
     return pair && pair_supported(net);
 }
+#endif
 
 template <bool BWD>
 static int dispatch(const DigsNet* net, const CUtensorMap& tmap, const Args& a, int want_jet, int want_lap, int passes,
                     cudaStream_t st) {
+#ifdef DIGS_WITH_PAIR
     if (use_pair(net)) return launch_pair(net, tmap, a, want_jet, want_lap, passes, BWD, st);
+#endif
     if (!want_jet) {
         if constexpr (BWD) { set_error("tc reverse needs jet channels"); return DIGS_EINVAL; }
         else return (passes == 3) ? launch_h<0, 0, 3, false>(net, tmap, a, st) : launch_h<0, 0, 1, false>(net, tmap, a, st);
@@ -705,18 +665,31 @@ static int dispatch(const DigsNet* net, const CUtensorMap& tmap, const Args& a, 
     return (passes == 3) ? launch_h<2, 0, 3, BWD>(net, tmap, a, st) : launch_h<2, 0, 1, BWD>(net, tmap, a, st);
 }
 
-// prepares the weight operands in `ws` and encodes the TMA map over them
-static int prepare(const DigsNet* net, void* ws, CUtensorMap* tmap, Args* a, cudaStream_t st) {
-    EncodeFn enc = get_encode();
-    if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return DIGS_ECUDA; }
-    char* w = reinterpret_cast<char*>(ws);
+// Weight operands of the tensor-core kernels: taken from net->prepared (digs_prepare_weights, hoisted out of the per-call
+// path) or, when that is NULL, built in `ws` by one k_tc_prep launch; then the TMA map over them is encoded.
+int run_prep(const DigsNet* net, void* dst, cudaStream_t st) {
+    char* w = reinterpret_cast<char*>(dst);
     __nv_bfloat16* Wq = reinterpret_cast<__nv_bfloat16*>(w);
     float* bias30 = reinterpret_cast<float*>(w + wq_bytes(net));
     float* w0_30 = reinterpret_cast<float*>(w + wq_bytes(net) + bias_bytes(net));
     PrepPtrs pp;
     for (int l = 0; l <= net->Lh + 1; ++l) { pp.W[l] = net->W[l]; pp.b[l] = net->b[l]; }
-    k_tc_prep<<<148 * 4, 256, 0, st>>>(pp, net->Lh, net->H, net->d, net->w0_stride, Wq, bias30, w0_30);
+    k_tc_prep<<<num_sms() * 4, 256, 0, st>>>(pp, net->Lh, net->H, net->d, net->w0_stride, Wq, bias30, w0_30);
     count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("tc prep launch: %s", cudaGetErrorString(e)); return DIGS_ECUDA; }
+    return DIGS_OK;
+}
+
+int prepare_weights(const DigsNet* net, void* ws, CUtensorMap* tmap, Prep* out, cudaStream_t st) {
+    EncodeFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return DIGS_ECUDA; }
+    char* w = net->prepared ? reinterpret_cast<char*>(const_cast<void*>(net->prepared)) : reinterpret_cast<char*>(ws);
+    if (!net->prepared) {
+        int rc = run_prep(net, ws, st);
+        if (rc) return rc;
+    }
+    __nv_bfloat16* Wq = reinterpret_cast<__nv_bfloat16*>(w);
     cuuint64_t gdim[2] = {(cuuint64_t)net->H, (cuuint64_t)4 * net->Lh * net->H};
     cuuint64_t gstr[1] = {(cuuint64_t)net->H * 2};
     cuuint32_t box[2] = {64, 128};
@@ -724,9 +697,18 @@ static int prepare(const DigsNet* net, void* ws, CUtensorMap* tmap, Args* a, cud
     CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Wq, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed (%d)", (int)r); return DIGS_ECUDA; }
+    out->bias30 = reinterpret_cast<float*>(w + wq_bytes(net));
+    out->w0_30 = reinterpret_cast<float*>(w + wq_bytes(net) + bias_bytes(net));
+    return DIGS_OK;
+}
+
+static int prepare(const DigsNet* net, void* ws, CUtensorMap* tmap, Args* a, cudaStream_t st) {
+    Prep p;
+    int rc = prepare_weights(net, ws, tmap, &p, st);
+    if (rc) return rc;
     a->Lh = net->Lh;
-    a->w0_30 = w0_30;
-    a->bias30 = bias30;
+    a->w0_30 = p.w0_30;
+    a->bias30 = p.bias30;
     a->w_last = net->W[net->Lh + 1];
     a->b_last = net->b[net->Lh + 1];
     a->head = net->head;

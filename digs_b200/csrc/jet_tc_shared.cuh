@@ -39,6 +39,51 @@ struct Args {
     int acc_smem;             // reverse: per-CTA shared-memory accumulators for the per-unit gradients (they fit)
 };
 
+template <int D, int LAP, int H_, int PASSES>
+struct Cfg {
+    static constexpr int C = 1 + D + LAP;
+    static constexpr int H = H_;
+    // One tile context per CTA.  (Two 64-column contexts ping-ponging on the MMA warp were measured SLOWER: a
+    // tcgen05.mma with N = 64 re-reads the 4 KB A tile from shared memory for half the math, and the operand fetch,
+    // not the tensor pipe, becomes the limit.)
+    static constexpr int N = (H_ > 256) ? 64 : 128;   // UMMA N = operand columns per tile (64 keeps X in smem at H=512)
+    static constexpr int GP = (C == 1) ? 16 : 4;      // points per epilogue group (one tcgen05.ld per channel)
+    static constexpr int T = (N / C) / GP * GP;       // points per tile (whole groups)
+    static constexpr int NGRP = T / GP;
+    static constexpr int MT = H / 128;                // UMMA M tiles
+    // Operand phases: the epilogue finishes the units of the first MT/2 M tiles (= the first half of the next layer's K
+    // range) before it touches the rest, so the MMA warp starts the next layer on those K slabs while the epilogue
+    // is still working on the second half.  Accumulators are double-buffered in TMEM for that.
+    static constexpr int NPH = (MT >= 2) ? 2 : 1;
+    static constexpr int MTP = MT / NPH;              // M tiles per phase
+    static constexpr int WQ = EPI_WARPS / 4;          // epilogue warps per TMEM lane quarter
+    static constexpr int NITEMS = MTP * NGRP;         // (M tile, point group) work items per quarter and phase
+    static constexpr int ROT = WQ / 2;                // item rotation between phases (balances 6 items over 4 warps)
+    static constexpr int NG = N / 64;                 // 64-column groups of the MN-major operand
+    static constexpr int SN = 1024;                   // byte stride between column groups   (descriptor LBO)
+    static constexpr int SK = NG * 1024;              // byte stride between 8-deep k groups (descriptor SBO)
+    static constexpr int B_PART = (H / 8) * SK;       // bytes of one operand part (hi or lo)
+    static constexpr int NPARTS = (PASSES == 3) ? 2 : 1;
+    static constexpr int B_BYTES = B_PART * NPARTS;
+    static constexpr int KSLABS = H / 64;
+    static constexpr int KS_PER_PH = KSLABS / NPH;
+    static constexpr int ACC_COLS = MT * N;           // TMEM columns of one accumulator buffer
+    static constexpr int TMEM_COLS = (2 * ACC_COLS <= 256) ? 256 : 512;
+    static constexpr int ETHREADS = EPI_WARPS * 32;
+    static constexpr int NUB = H / 32;                // 32-unit blocks
+    static constexpr int OFF_RING = B_BYTES;
+    static constexpr int OFF_XYZ = OFF_RING + STAGES * STAGE_BYTES;      // [N*3] floats
+    static constexpr int OFF_UBAR = OFF_XYZ + N * 3 * 4;                  // [N] floats
+    static constexpr int OFF_BAR = OFF_UBAR + N * 4;
+    static constexpr int OFF_HEAD = OFF_BAR + 256;                        // forward: [NUB][N] floats of last-layer partial sums
+    static constexpr int OFF_ACC = OFF_HEAD;                              // reverse: [(Lh+1) db | 3 dW0 | dw_last][H] floats (optional)
+    static constexpr int SMEM_BYTES = OFF_HEAD + NUB * N * 4 + 1024;      // + alignment slack; the reverse kernel adds the accumulators
+    static_assert(H == 128 || H == 256 || H == 512, "H must be 128, 256 or 512");
+    static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
+    static_assert(NITEMS >= WQ, "every epilogue warp needs at least one item per phase (it arrives on b_ready after its last)");
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
 // sin/cos of a phase of any magnitude: two-constant Cody-Waite reduction to [-pi, pi], then MUFU
 __device__ __forceinline__ void sincos_reduced(float t, float& s, float& c) {
     const float magic = 12582912.f;  // 1.5 * 2^23: round-to-nearest-integer trick
@@ -90,6 +135,14 @@ __device__ __forceinline__ void point_coords(const PreSrc& s, int64_t gp, float&
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// weight operands (jet_tc.cu)
+struct Prep {
+    const float* bias30;
+    const float* w0_30;
+};
+int run_prep(const DigsNet* net, void* dst, cudaStream_t st);
+int prepare_weights(const DigsNet* net, void* ws, CUtensorMap* tmap, Prep* out, cudaStream_t st);
 
 // paired-CTA variant of the network kernel (jet_tc_pair.cu); H = 256 only
 bool pair_supported(const DigsNet* net);

@@ -10,6 +10,11 @@
 
 namespace digs {
 
+__global__ void k_step_inc(int32_t* step_dev, float* sumsq) {
+    *step_dev += 1;
+    *sumsq = 0.f;
+}
+
 __global__ void __launch_bounds__(256) k_sumsq(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
     float a = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -31,11 +36,16 @@ __global__ void __launch_bounds__(256) k_sumsq(const float* __restrict__ g, int6
 __global__ void __launch_bounds__(256) k_clip_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, float lr, float b1, float b2,
                                                    float eps, float max_norm, float bc1, float bc2_sqrt,
-                                                   const float* __restrict__ sumsq) {
+                                                   const float* __restrict__ sumsq, const int32_t* __restrict__ step_dev) {
     float coef = 1.f;
     if (max_norm > 0.f) {
         float c = max_norm / (sqrtf(*sumsq) + 1e-6f);
-        coef = c < 1.f ? c : 1.f;
+        coef = c > 1.f ? 1.f : c;                    // torch.clamp(c, max=1.0): a NaN norm propagates into the gradients
+    }
+    if (step_dev) {                                  // replayable form: the step count is read from device memory
+        const float t = (float)(*step_dev);          // already incremented for this step by k_sumsq_step
+        bc1 = 1.f - powf(b1, t);
+        bc2_sqrt = sqrtf(1.f - powf(b2, t));
     }
     const float step_size = lr / bc1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -51,18 +61,25 @@ __global__ void __launch_bounds__(256) k_clip_adam(float* __restrict__ p, float*
 }
 
 int clip_adam(float* p, float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float max_norm,
-              int step, float* scratch, cudaStream_t st) {
+              int step, int32_t* step_dev, float* scratch, cudaStream_t st) {
     if (n == 0) return DIGS_OK;
     int blocks = (int)((n + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    if (max_norm > 0.f) {
+    const int cap = tcpath::num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (step_dev) {
+        k_step_inc<<<1, 1, 0, st>>>(step_dev, scratch);
+        count_launch();
+    } else if (max_norm > 0.f) {
         cudaMemsetAsync(scratch, 0, sizeof(float), st);
+    }
+    if (max_norm > 0.f) {
         k_sumsq<<<blocks, 256, 0, st>>>(g, n, scratch);
         count_launch();
     }
-    double bc1 = 1.0 - pow((double)b1, (double)step);
-    double bc2 = 1.0 - pow((double)b2, (double)step);
-    k_clip_adam<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, max_norm, (float)bc1, (float)sqrt(bc2), scratch);
+    double bc1 = 1.0 - pow((double)b1, (double)(step > 0 ? step : 1));
+    double bc2 = 1.0 - pow((double)b2, (double)(step > 0 ? step : 1));
+    k_clip_adam<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, max_norm, (float)bc1, (float)sqrt(bc2), scratch,
+                                        step_dev);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("clip_adam launch: %s", cudaGetErrorString(e)); return DIGS_ECUDA; }

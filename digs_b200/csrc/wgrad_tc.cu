@@ -175,11 +175,13 @@ int wgrad(const DigsNet* net, const __nv_bfloat16* GP_words, const __nv_bfloat16
     if (ns > kblocks) ns = (int)kblocks;
     a.nsplit = ns;
     for (int l = 0; l <= Lh + 1; ++l) a.dW[l] = grads->dW[l];
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};      // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
         if (e != cudaSuccess) { set_error("tc wgrad: smem attribute: %s", cudaGetErrorString(e)); return DIGS_ECUDA; }
-        attr_set = true;
+        attr_set[dev & 63] = true;
     }
     dim3 grid(ns, n_mtiles * a.n_ntiles, Lh);
     k_tc_wgrad<<<grid, WG_THREADS, WG_SMEM, st>>>(tG, tA, a);

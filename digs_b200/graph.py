@@ -1,59 +1,91 @@
-"""The hot-path step captured once into a CUDA graph.
+"""The training iteration captured once into a CUDA graph.
 
 A reference training iteration issues ~900 kernel launches plus nine `.item()` syncs for logging
-(train_surface_reconstruction.py:121-132, utils/utils.py:30-36).  The fused path needs about a dozen launches, at
-which point Python / launch latency is comparable to the GPU time of a 30 000-point step.  `GraphedStep` records
+(train_surface_reconstruction.py:114-158, utils/utils.py:30-36).  `GraphedStep` records
 
-    flat-gradient zero-fill -> DiGSNetwork.forward (both clouds) -> DiGSLoss.forward -> loss.backward()
+    [batch sampling] -> gradient zero-fill -> weight-operand preparation -> fused step (forward jets of both clouds,
+    DiGSLoss, reverse pass: digs_step_fused, two launches) -> [gradient all-reduce over ranks] -> [clip + Adam]
 
-into ONE CUDA graph over static input buffers and replays it per iteration.  Everything that changes between
-iterations stays outside the graph or in device memory:
-  * the point batches are copied into the static buffers (host or device source, asynchronously);
+into ONE CUDA graph over static buffers and replays it per iteration with zero host synchronisations.  The parts in
+brackets are optional (`sampler=`, a process group with more than one rank, `optimizer=`).  Everything that changes
+between iterations lives in device memory:
+  * the point batch is copied into the static buffers asynchronously (or drawn inside the graph by a DeviceSampler);
   * the loss weights -- `update_div_weight` rewrites weights[4] every iteration (models/losses.py:208-224) -- are
-    re-read from a small device tensor at every replay (digs_loss_fused_dw);
-  * the gradient all-reduce (when sharded over ranks), clipping and the optimizer run after the replay as usual.
-Gradients land in a `digs_b200.dist.FlatGrads` buffer (every parameter's .grad is a view of it).
+    re-read from a small device tensor at every replay;
+  * the Adam step count is advanced on the device (FusedClipAdam(device_step=True)).
+Precision mode fp32 and the loss variants outside the fused kernel take the two-call path
+(DiGSNetwork.forward -> DiGSLoss.forward -> backward) inside the same graph.
+Gradients land in a `digs_b200.dist.FlatGrads` buffer (every parameter's .grad is a view of it); the eight loss scalars
+ride in its trailing slots through the all-reduce, so sharded runs report the global loss without an extra collective.
 """
 import torch
+import torch.distributed as dist
 
 from .dist import FlatGrads
+from .jet import bump_param_epoch
+from .step import fused_step, fused_step_supported
 
 
 class GraphedStep:
-    def __init__(self, net, criterion, n_mnfld, n_nonmnfld, batch=1, flat=None, warmup=3, sampler=None):
+    def __init__(self, net, criterion, n_mnfld, n_nonmnfld, batch=1, flat=None, warmup=3, sampler=None, optimizer=None,
+                 latent_table=None, group=None, fused=None):
         params = list(net.parameters())
         dev = params[0].device
         if dev.type != "cuda":
             raise RuntimeError("digs_b200.GraphedStep needs the network on a CUDA device -- no CPU fallback")
-        if net.encoder_type == "autodecoder":
-            raise NotImplementedError("GraphedStep covers the single-shape recipes (encoder_type='none')")
         d = net.in_dim
-        self.net, self.criterion = net, criterion
+        self.net, self.criterion, self.optimizer, self.group = net, criterion, optimizer, group
+        self.autodecoder = net.encoder_type == "autodecoder"
+        if self.autodecoder and latent_table is None:
+            raise ValueError("GraphedStep: an auto-decoder network needs latent_table=(num_shapes, latent_size)")
+        self.fused = fused_step_supported(net, criterion) if fused is None else bool(fused)
+        if self.fused and not fused_step_supported(net, criterion):
+            raise ValueError("GraphedStep(fused=True): precision mode / loss type outside digs_step_fused")
+        if self.autodecoder and not self.fused:
+            raise NotImplementedError("GraphedStep: the auto-decoder recipe is captured through the fused step only")
         self.sampler = sampler          # optional digs_b200.DeviceSampler: the batch is then drawn INSIDE the graph
         if sampler is not None and (batch != 1 or sampler.n_points != n_mnfld or n_mnfld != n_nonmnfld):
             raise ValueError("GraphedStep: the sampler draws one cloud of n_points surface + n_points off-surface samples")
+        if optimizer is not None:
+            if getattr(optimizer, "_step_dev", None) is None:
+                raise ValueError("GraphedStep(optimizer=...): needs digs_b200.FusedClipAdam(..., device_step=True)")
+            flat = optimizer.flat_grads if flat is None else flat
+            if flat is not optimizer.flat_grads:
+                raise ValueError("GraphedStep: `flat` must be the optimizer's FlatGrads buffer")
         self.flat = flat if flat is not None else FlatGrads(params, extra=8)
-        net.decoder.fc_block.accumulate_grads_in_place = True
-        self.mnfld = torch.zeros(batch, n_mnfld, d, device=dev).requires_grad_()
-        self.nonmnfld = torch.zeros(batch, n_nonmnfld, d, device=dev).requires_grad_()
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        fc = net.decoder.fc_block
+        self.mnfld = torch.zeros(batch, n_mnfld, d, device=dev)
+        self.nonmnfld = torch.zeros(batch, n_nonmnfld, d, device=dev)
         self.normals = torch.zeros(batch, n_mnfld, d, device=dev)
+        self.latent_table = latent_table
+        self.latent_grad = None
+        if self.autodecoder:
+            if latent_table.device != dev or latent_table.dim() != 2:
+                raise ValueError("GraphedStep: latent_table must be a (num_shapes, latent_size) tensor on the network's device")
+            self.indices = torch.zeros(batch, dtype=torch.long, device=dev)
+            self.latent_grad = torch.zeros_like(latent_table)         # dense, like Adam over the whole table
+            if latent_table.requires_grad:
+                latent_table.grad = self.latent_grad                  # train_shapespace.py:92-103: Adam over {net, table}
         self._w_host = torch.zeros(8, 6, dtype=torch.float32).pin_memory()   # ring: an in-flight async copy is never overwritten
         self._w_slot = 0
         self._w_dev = torch.zeros(6, dtype=torch.float32, device=dev)
-        criterion.device_weights = self._w_dev
         self._push_weights()
+        self._param_ptrs = [p.data_ptr() for p in params]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
-                self._body()
+                self._body(warm=True)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         from . import _lib
         before = _lib.lib().digs_launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss_dict = self._body()
+        fc.invalidate_prepared()        # the operand preparation must be recorded inside the graph
+        mode = "thread_local" if self.world > 1 else "global"   # NCCL's watchdog thread touches CUDA while we capture
+        with torch.cuda.graph(self.graph, capture_error_mode=mode):
+            self.loss_dict = self._body(warm=False)
         self.launches_per_step = int(_lib.lib().digs_launch_count() - before)   # library kernels recorded in the graph
         self.loss_dict = {k: v.detach() for k, v in self.loss_dict.items()}
 
@@ -67,24 +99,68 @@ class GraphedStep:
             slot[i] = float(w[i])
         self._w_dev.copy_(slot, non_blocking=True)
 
-    def _body(self):
-        if self.sampler is not None:
-            self.sampler.sample_into(self.mnfld, self.normals, self.nonmnfld)
-        self.flat.zero_()
-        out = self.net(self.nonmnfld, self.mnfld)
-        loss_dict, _ = self.criterion(out, self.mnfld, self.nonmnfld, self.normals)
-        loss_dict["loss"].backward()
-        return loss_dict
+    def _body(self, warm):
+        """One iteration.  The device-weights / in-place-accumulation switches are scoped to this body: eager calls of
+        the same criterion / network outside the graph keep their normal behaviour."""
+        crit, fc = self.criterion, self.net.decoder.fc_block
+        had_dw = getattr(crit, "device_weights", None)
+        had_acc = fc.accumulate_grads_in_place
+        crit.device_weights = self._w_dev
+        fc.accumulate_grads_in_place = True
+        try:
+            if self.sampler is not None:
+                self.sampler.sample_into(self.mnfld, self.normals, self.nonmnfld)
+            self.flat.zero_()
+            if self.fused:
+                latent = None
+                if self.autodecoder:
+                    latent = self.latent_table.detach().index_select(0, self.indices)      # train_shapespace.py:122
+                loss_dict, _, lat_grad = fused_step(self.net, crit, self.mnfld, self.nonmnfld, self.normals, latent=latent)
+                if self.autodecoder:
+                    self.latent_grad.zero_()
+                    self.latent_grad.index_add_(0, self.indices, lat_grad)
+            else:
+                m = self.mnfld.detach().requires_grad_()
+                nm = self.nonmnfld.detach().requires_grad_()
+                out = self.net(nm, m)
+                loss_dict, _ = crit(out, m, nm, self.normals)
+                loss_dict["loss"].backward()
+            # the 8 scalars ride in the flat buffer's trailing slots (one collective for gradients and loss terms)
+            keys = ("loss", "sdf_term", "inter_term", "latent_reg_term", "eikonal_term", "normals_loss", "div_loss", "curv_loss")
+            ex = self.flat.extra
+            for i, k in enumerate(keys):
+                ex[i:i + 1].copy_(loss_dict[k].detach().reshape(-1)[:1])
+            if self.world > 1:
+                dist.all_reduce(self.flat.flat, op=dist.ReduceOp.SUM, group=self.group)
+                if self.autodecoder:
+                    dist.all_reduce(self.latent_grad, op=dist.ReduceOp.SUM, group=self.group)
+            if self.optimizer is not None:
+                self.optimizer.step()
+            return {k: ex[i] for i, k in enumerate(keys)}
+        finally:
+            if had_dw is None:
+                if hasattr(crit, "device_weights"):
+                    del crit.device_weights
+            else:
+                crit.device_weights = had_dw
+            fc.accumulate_grads_in_place = had_acc
 
     @torch.no_grad()
-    def step(self, mnfld_points=None, nonmnfld_points=None, mnfld_normals=None):
+    def step(self, mnfld_points=None, nonmnfld_points=None, mnfld_normals=None, indices=None):
         """Copies one batch into the static buffers (or, with a sampler, lets the graph draw it), replays the graph.
-        Returns the dict of 8 loss tensors (static device tensors, overwritten by the next call); parameter gradients
-        are in `self.flat` / every `.grad`."""
+        Returns the dict of 8 loss tensors (static device tensors, overwritten by the next call; summed over ranks when
+        sharded); parameter gradients are in `self.flat` / every `.grad`, latent-table gradients in `self.latent_grad`."""
+        if [p.data_ptr() for p in self.net.parameters()] != self._param_ptrs:
+            raise RuntimeError("digs_b200.GraphedStep: parameter storage moved since capture (construct FusedClipAdam / "
+                               "re-point .data BEFORE GraphedStep) -- the graph would read stale memory")
         if self.sampler is None:
             self.mnfld.copy_(mnfld_points, non_blocking=True)
             self.nonmnfld.copy_(nonmnfld_points, non_blocking=True)
             self.normals.copy_(mnfld_normals, non_blocking=True)
+        if self.autodecoder:
+            self.indices.copy_(indices, non_blocking=True)
         self._push_weights()
         self.graph.replay()
+        if self.optimizer is not None:
+            bump_param_epoch()      # the replayed optimizer wrote the parameters: cached operand copies are stale for eager calls
         return self.loss_dict

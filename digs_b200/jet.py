@@ -18,8 +18,10 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """Current stream of `device` (default: the current device).  Kernel launches are wrapped in
+    torch.cuda.device(tensor.device) by the callers, so the stream and the launch device always agree."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _require_cuda(t, name):
@@ -35,6 +37,7 @@ class NetSpec:
     def __init__(self, d, H, Lh, head, radius, scale, w0_stride):
         self.d, self.H, self.Lh, self.head = int(d), int(H), int(Lh), int(head)
         self.radius, self.scale, self.w0_stride = float(radius), float(scale), int(w0_stride)
+        self.prepared = None        # optional uint8 tensor filled by digs_prepare_weights for the current parameter values
 
     def c_net(self, params):
         """params: flat list [W0, b0, W1, b1, ...] of contiguous fp32 CUDA tensors."""
@@ -52,7 +55,35 @@ class NetSpec:
                 raise RuntimeError("digs_b200: parameters must be contiguous")
             net.W[l] = W.data_ptr()
             net.b[l] = b.data_ptr()
+        net.prepared = None if self.prepared is None else self.prepared.data_ptr()
         return net
+
+
+# Bumped by code that changes parameter VALUES behind autograd's back (raw kernels writing through data pointers, e.g.
+# FusedClipAdam): tensor._version does not see those writes, and the prepared-operand cache keys on both.
+PARAM_EPOCH = [0]
+
+
+def bump_param_epoch():
+    PARAM_EPOCH[0] += 1
+
+
+def prepare_weights(spec, params, mode, buf=None):
+    """Tensor-core operand copies of the weights (digs_prepare_weights); returns the buffer (None in fp32 mode)."""
+    L = _lib.lib()
+    spec_prepared, spec.prepared = spec.prepared, None
+    net = spec.c_net(params)
+    spec.prepared = spec_prepared
+    nbytes = L.digs_prepared_bytes(ctypes.byref(net), mode)
+    if nbytes == 0:
+        return None
+    dev = params[0].device
+    if buf is None or buf.numel() < nbytes or buf.device != dev:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.digs_prepare_weights(ctypes.byref(net), _ptr(buf), buf.numel(), mode, _stream(dev))
+    _lib.check(rc, "prepare_weights")
+    return buf
 
 
 def _scratch(nbytes, device):
@@ -78,9 +109,10 @@ def jet_forward_raw(spec, params, xyz, shape_bias, pts_per_shape, want_lap, save
     if n > 0 and wbytes == 0:
         _lib.check(-1, "forward_workspace_bytes")
     ws = _scratch(wbytes, dev)
-    rc = L.digs_jet_forward(ctypes.byref(net), _ptr(xyz), n, stride, _ptr(shape_bias), int(pts_per_shape),
-                            int(want_lap), _ptr(f), _ptr(g), _ptr(lap), _ptr(saved), sbytes, _ptr(ws), wbytes,
-                            mode, _stream())
+    with torch.cuda.device(dev):
+        rc = L.digs_jet_forward(ctypes.byref(net), _ptr(xyz), n, stride, _ptr(shape_bias), int(pts_per_shape),
+                                int(want_lap), _ptr(f), _ptr(g), _ptr(lap), _ptr(saved), sbytes, _ptr(ws), wbytes,
+                                mode, _stream(dev))
     _lib.check(rc, "jet_forward")
     return f, g, lap, saved
 
@@ -106,9 +138,10 @@ def jet_backward_raw(spec, params, xyz, shape_bias, pts_per_shape, want_lap, f_b
     for t in (f_bar, g_bar, l_bar):
         if t is not None:
             _require_cuda(t, "adjoint seed")
-    rc = L.digs_jet_backward(ctypes.byref(net), _ptr(xyz), n, stride, _ptr(shape_bias), int(pts_per_shape),
-                             int(want_lap), _ptr(f_bar), _ptr(g_bar), _ptr(l_bar), _ptr(saved), saved.numel(),
-                             _ptr(ws), wbytes, ctypes.byref(gr), _ptr(sb_grad), mode, _stream())
+    with torch.cuda.device(dev):
+        rc = L.digs_jet_backward(ctypes.byref(net), _ptr(xyz), n, stride, _ptr(shape_bias), int(pts_per_shape),
+                                 int(want_lap), _ptr(f_bar), _ptr(g_bar), _ptr(l_bar), _ptr(saved), saved.numel(),
+                                 _ptr(ws), wbytes, ctypes.byref(gr), _ptr(sb_grad), mode, _stream(dev))
     _lib.check(rc, "jet_backward")
     return grad_out, sb_grad
 
@@ -121,8 +154,9 @@ def value_forward_raw(spec, params, xyz, shape_bias, pts_per_shape, mode):
     f = torch.empty(n, dtype=torch.float32, device=xyz.device)
     wbytes = L.digs_value_workspace_bytes(ctypes.byref(net), n, mode)
     ws = _scratch(wbytes, xyz.device)
-    rc = L.digs_value_forward(ctypes.byref(net), _ptr(xyz), n, stride, _ptr(shape_bias), int(pts_per_shape),
-                              _ptr(f), _ptr(ws), wbytes, mode, _stream())
+    with torch.cuda.device(xyz.device):
+        rc = L.digs_value_forward(ctypes.byref(net), _ptr(xyz), n, stride, _ptr(shape_bias), int(pts_per_shape),
+                                  _ptr(f), _ptr(ws), wbytes, mode, _stream(xyz.device))
     _lib.check(rc, "value_forward")
     return f
 

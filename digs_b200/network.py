@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import jet as _jet
 from .jet import JetFunction, JetPairFunction, NetSpec, value_forward_raw
 
 OMEGA = 30.0
@@ -159,7 +160,28 @@ class FCBlock(nn.Module):
         spec = NetSpec(self.spatial_dim, lins[0].out_features, len(lins) - 2, head, radius, scale,
                        lins[0].in_features)
         spec.accumulate_in_place = self.accumulate_grads_in_place
+        spec.prepared = self._prepared_operands(spec)
         return spec
+
+    def invalidate_prepared(self):
+        """Forget the cached tensor-core operand copies (e.g. before a CUDA-graph capture, so that the preparation
+        launch is recorded inside the graph and replayed with it)."""
+        self._prep_key = None
+
+    def _prepared_operands(self, spec):
+        """bf16 hi/lo copies of 30 W and (30 W)^T for the tcgen05 kernels, rebuilt only when a parameter changed
+        (tensor versions + jet.PARAM_EPOCH); one launch instead of one per forward / backward / query call."""
+        mode = self.mode()
+        if mode == _lib.MODE_FP32:
+            return None
+        params = self.flat_params()
+        if not params[0].is_cuda:
+            return None
+        key = (mode, _jet.PARAM_EPOCH[0], tuple((p.data_ptr(), p._version) for p in params))
+        if key != getattr(self, "_prep_key", None):
+            self._prep_buf = _jet.prepare_weights(spec, [p.detach() for p in params], mode, getattr(self, "_prep_buf", None))
+            self._prep_key = key
+        return self._prep_buf
 
     def mode(self):
         return _lib.MODES[self.precision]
@@ -173,7 +195,14 @@ class FCBlock(nn.Module):
         if lat_dim != self.linears()[0].in_features - d:
             raise RuntimeError("digs_b200: input width %d does not match the first layer" % coords.shape[1])
         if pts_per_shape is None:
-            pts_per_shape = coords.shape[0]
+            # decoder(points) called directly (utils/utils.py:345-348 repeats ONE latent over the chunk): rows may
+            # in principle carry different latents -- BatchLinear would use each row's own (models/DiGS.py:142-151).
+            # One device comparison decides between the per-shape fold and a per-row bias (never a wrong latent).
+            full = coords[:, d:]
+            if coords.shape[0] > 1 and not bool((full == full[:1]).all()):
+                pts_per_shape = 1
+            else:
+                pts_per_shape = coords.shape[0]
         # the latent is constant over the points of a shape (train_shapespace.py:124-128,
         # utils/utils.py:345-346), so it folds into a per-shape bias of layer 0
         lat = coords[::pts_per_shape, d:]
@@ -259,7 +288,14 @@ class DiGSNetwork(nn.Module):
             f, g, lap = fc.jet(flat, want_lap=want_lap, pts_per_shape=npts)
             return (f.reshape(bs, npts), g.reshape(bs, npts, self.in_dim),
                     None if lap is None else lap.reshape(bs, npts))
-        return fc(flat).reshape(bs, npts), None, None
+        if torch.is_grad_enabled() and any(p.requires_grad for p in fc.parameters()):
+            f, _, _ = fc.jet(flat, want_lap=False, pts_per_shape=npts)      # value with autograd to the parameters
+            return f.reshape(bs, npts), None, None
+        flat = flat.contiguous()
+        sb, pps = fc._split_latent(flat, npts)                               # each cloud of the batch has its own latent
+        with torch.no_grad():
+            f = value_forward_raw(fc.spec(), [p.detach() for p in fc.flat_params()], flat, sb, pps, fc.mode())
+        return f.reshape(bs, npts), None, None
 
     def forward(self, non_mnfld_pnts, mnfld_pnts=None):
         latent = latent_reg = None

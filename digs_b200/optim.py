@@ -11,11 +11,11 @@ import torch
 
 from . import _lib
 from .dist import FlatGrads
-from .jet import _ptr, _stream
+from .jet import _ptr, _stream, bump_param_epoch
 
 
 class FusedClipAdam:
-    def __init__(self, params, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, max_norm=10.0, flat_grads=None):
+    def __init__(self, params, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, max_norm=10.0, flat_grads=None, device_step=False):
         self.params = list(params)
         if not self.params or not self.params[0].is_cuda:
             raise RuntimeError("digs_b200.FusedClipAdam needs CUDA parameters -- no CPU fallback")
@@ -35,6 +35,10 @@ class FusedClipAdam:
         self.exp_avg_sq = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self._scratch = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_count = 0
+        # device_step: the Adam step count lives in device memory and is advanced by the kernel itself, so step() can
+        # be recorded into a CUDA graph (digs_b200.GraphedStep(optimizer=...)) and replayed
+        self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev) if device_step else None
+        bump_param_epoch()          # parameter storage moved into the flat buffer
 
     def zero_grad(self):
         self.flat_grads.zero_()
@@ -42,7 +46,16 @@ class FusedClipAdam:
     @torch.no_grad()
     def step(self):
         self.step_count += 1
-        rc = _lib.lib().digs_clip_adam(_ptr(self.flat_params), _ptr(self.flat_grads.flat), _ptr(self.exp_avg),
-                                       _ptr(self.exp_avg_sq), self.n, self.lr, self.betas[0], self.betas[1], self.eps,
-                                       self.max_norm, self.step_count, _ptr(self._scratch), _stream())
+        dev = self.flat_params.device
+        with torch.cuda.device(dev):
+            if self._step_dev is not None:
+                rc = _lib.lib().digs_clip_adam_dev(_ptr(self.flat_params), _ptr(self.flat_grads.flat), _ptr(self.exp_avg),
+                                                   _ptr(self.exp_avg_sq), self.n, self.lr, self.betas[0], self.betas[1],
+                                                   self.eps, self.max_norm, _ptr(self._step_dev), _ptr(self._scratch),
+                                                   _stream(dev))
+            else:
+                rc = _lib.lib().digs_clip_adam(_ptr(self.flat_params), _ptr(self.flat_grads.flat), _ptr(self.exp_avg),
+                                               _ptr(self.exp_avg_sq), self.n, self.lr, self.betas[0], self.betas[1],
+                                               self.eps, self.max_norm, self.step_count, _ptr(self._scratch), _stream(dev))
         _lib.check(rc, "clip_adam")
+        bump_param_epoch()          # the kernel wrote the parameters through raw pointers: tensor versions did not move

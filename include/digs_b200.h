@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DIGS_ABI_VERSION 1
+#define DIGS_ABI_VERSION 2
 #define DIGS_MAX_LAYERS 18 /* Lh + 2 <= 18 */
 
 /* error codes */
@@ -68,6 +68,10 @@ typedef struct DigsNet {
     int32_t reserved;
     const float* W[DIGS_MAX_LAYERS]; /* W[0] (H,w0_stride); W[1..Lh] (H,H); W[Lh+1] (1,H) */
     const float* b[DIGS_MAX_LAYERS]; /* b[0..Lh] (H); b[Lh+1] (1) */
+    /* NULL, or digs_prepared_bytes() bytes filled by digs_prepare_weights() for THESE parameter values: the
+     * tensor-core modes then skip their per-call operand preparation (bf16 hi/lo copies of 30 W and (30 W)^T).
+     * The caller re-runs digs_prepare_weights after every parameter update (ABI 2). */
+    const void* prepared;
 } DigsNet;
 
 /* Gradient destinations, same indexing as DigsNet.W/b.  Kernels ACCUMULATE (+=) into them.
@@ -90,6 +94,11 @@ size_t digs_forward_workspace_bytes(const DigsNet* net, int64_t n, int want_lap,
 size_t digs_backward_workspace_bytes(const DigsNet* net, int64_t n, int want_lap, int precision_mode);
 size_t digs_value_workspace_bytes(const DigsNet* net, int64_t n, int precision_mode);
 size_t digs_grid_workspace_bytes(const DigsNet* net, int precision_mode);
+
+/* Tensor-core operand preparation, hoisted out of the per-call path (DIGS_MODE_BF16X2 / DIGS_MODE_BF16; a no-op
+ * returning 0 bytes in DIGS_MODE_FP32).  One launch; see DigsNet.prepared. */
+size_t digs_prepared_bytes(const DigsNet* net, int precision_mode);
+int digs_prepare_weights(const DigsNet* net, void* prepared, size_t prepared_bytes, int precision_mode, void* stream);
 
 /* Forward jet of one point cloud.
  *  xyz          (n, xyz_stride) fp32, the first d columns are the coordinates.
@@ -134,6 +143,39 @@ int digs_loss_fused_dw(const float* f_m, const float* g_m, int64_t nm, const flo
                        float* fbar_m, float* gbar_m, float* fbar_n, float* gbar_n, float* lbar_n,
                        float* terms_out, void* stream);
 
+/* ---- The whole hot-path step of one batch as TWO launches (tensor-core modes) ---------------------------------------
+ * Replaces, for one iteration, train_surface_reconstruction.py:121-128 (train_basic_shape.py:105-132,
+ * train_shapespace.py:130-145): DiGSNetwork.forward on both clouds, DiGSLoss.forward and loss.backward().
+ * Every DiGS loss term is a mean of per-point functions (models/losses.py:107-168), so a point's adjoint seeds need only
+ * its own (f, grad f, lap f) and global constants: a persistent kernel walks point tiles and runs, per tile,
+ *   forward jet -> output head -> loss terms + adjoint seeds -> reverse jet
+ * with the tile's pre-activations parked in a per-CTA scratch ring that stays in L2; only the two operand streams of the
+ * weight-gradient GEMM (layer inputs, adjoints) reach HBM, and one GEMM launch over both clouds finishes the step.
+ *   nonmnfld (nn, xyz_stride) / mnfld (nm, xyz_stride): the first d columns are coordinates; normals (nm, d) or NULL.
+ *   shape_bias_n / shape_bias_m: NULL, or (n_shapes, H) per-shape layer-0 bias (auto-decoder), points_per_shape each;
+ *   sb_grad_n / sb_grad_m (n_shapes, H) accumulate its gradient.
+ *   cfg: loss configuration (weights on the host or, for CUDA-graph replays, in device memory; global point counts).
+ *   outputs f_n (nn), g_n (nn,d), lap_n (nn or NULL), f_m (nm), g_m (nm,d); terms_out[8] as digs_loss_fused (accumulated).
+ *   grads: accumulated (+=) like digs_jet_backward.
+ * DIGS_MODE_FP32 returns DIGS_ENOTIMPL (the two-call API covers it). */
+typedef struct DigsLossCfg {
+    float weights[6];            /* sdf, inter, normal, eikonal, div, latent (host copy) */
+    const float* weights_device; /* NULL, or 6 floats in device memory read at kernel time (overrides weights) */
+    int32_t add_normal;          /* loss type adds the normal term (siren, siren_w_div) */
+    int32_t use_div;             /* loss type has 'div' */
+    int32_t div_l2;              /* 0 = l1, 1 = l2 */
+    float div_clamp;
+    int64_t Nm_total, Nn_total;  /* GLOBAL point counts of the means (>= local counts when sharded over ranks) */
+} DigsLossCfg;
+size_t digs_step_workspace_bytes(const DigsNet* net, int64_t nn, int64_t nm, int want_lap, int precision_mode);
+int digs_step_fused(const DigsNet* net, const float* nonmnfld, int64_t nn, const float* mnfld, int64_t nm,
+                    const float* normals, int64_t xyz_stride,
+                    const float* shape_bias_n, const float* shape_bias_m, int64_t pts_per_shape_n, int64_t pts_per_shape_m,
+                    int want_lap, const DigsLossCfg* cfg,
+                    float* f_n, float* g_n, float* lap_n, float* f_m, float* g_m, float* terms_out,
+                    const DigsGrads* grads, float* sb_grad_n, float* sb_grad_m,
+                    void* workspace, size_t workspace_bytes, int precision_mode, void* stream);
+
 /* decoder(points) -> (n) values, no derivative channels, nothing saved. */
 int digs_value_forward(const DigsNet* net, const float* xyz, int64_t n, int64_t xyz_stride,
                        const float* shape_bias, int64_t pts_per_shape, float* f,
@@ -158,10 +200,14 @@ int digs_sample_batch(const float* cloud, const float* normals, int64_t n_cloud,
 
 /* Optimizer tail over flat buffers: clip_grad_norm_(params, max_norm) (train_surface_reconstruction.py:130; the loops
  * hard-code 10.) followed by Adam.step() (train_surface_reconstruction.py:63,132).  grads are rescaled in place like
- * clip_grad_norm_ does; max_norm <= 0 skips clipping (train_basic_shape.py:132-133 does not clip).  step is the 1-based
- * Adam step count; scratch is one device float. */
+ * clip_grad_norm_ does (a NaN / Inf norm propagates into them, as in torch); max_norm <= 0 skips clipping
+ * (train_basic_shape.py:132-133 does not clip).  step is the 1-based Adam step count; scratch is one device float. */
 int digs_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                    float beta2, float eps, float max_norm, int step, float* scratch, void* stream);
+/* Same, CUDA-graph replayable: the Adam step count lives in device memory (step_counter: one int32, zero-initialised
+ * by the caller); the kernel increments it and derives the bias corrections itself. */
+int digs_clip_adam_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float max_norm, int32_t* step_counter, float* scratch, void* stream);
 
 /* Iso-surface extraction on a dense fp32 volume in memory order (n0, n1, n2), n2 fastest: replaces
  * skimage.measure.marching_cubes(volume, level, spacing) + the origin shift of utils/utils.py:354-358.  Vertices sit on

@@ -4,14 +4,45 @@ The reference's ``utils/utils.py`` imports five packages that are not installed 
 (tensorboardX, plyfile, skimage, plotly, trimesh; utils/utils.py:4-16).  None of them is
 touched by the hot path, so empty stub modules are enough.
 
-``/root/reference`` exists only in the build container; ``available()`` is False on the
-GPU box and every caller must then fall back to the committed golden fixtures.
+``/root/reference`` exists only in the build container.  ``__graft_entry__.build()`` installs the three
+module directories the hot path touches (models/, utils/ -- unmodified) into the git-ignored
+``baseline/_ref/`` so that the *reference arm* of bench.py can time the real reference modules on the GPU
+box's host cores (and, for context, through stock PyTorch CUDA).  The -m gpu tests and smoke() never import
+it: they use the committed golden fixtures.
 """
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DIGS_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+INSTALLED_ROOT = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+
+
+def _pick_root():
+    env = os.environ.get("DIGS_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", INSTALLED_ROOT):
+        if os.path.isfile(os.path.join(cand, "models", "DiGS.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
+
+
+def install(dst=INSTALLED_ROOT, src="/root/reference"):
+    """Copy the unmodified reference modules of the hot path (models/, utils/) into baseline/_ref (git-ignored)."""
+    import shutil
+    if not os.path.isfile(os.path.join(src, "models", "DiGS.py")):
+        return False
+    for sub in ("models", "utils"):
+        shutil.copytree(os.path.join(src, sub), os.path.join(dst, sub), dirs_exist_ok=True,
+                        ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+    for f in ("LICENCE", "README.md"):
+        if os.path.isfile(os.path.join(src, f)):
+            shutil.copy(os.path.join(src, f), os.path.join(dst, f))
+    return True
 
 
 def available() -> bool:

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_loads_and_exports_every_declared_symbol():
     L = _lib.lib()
-    assert L.digs_abi_version() == 1
+    assert L.digs_abi_version() == 2
     header = open(os.path.join(ROOT, "include", "digs_b200.h")).read()
     declared = set(re.findall(r"\b(digs_[a-z0-9_]+)\s*\(", header))
     assert declared, "no entry points found in the header"
