@@ -59,7 +59,8 @@ EXPORTS = (
     "digs_mt_classify", "digs_mt_emit", "digs_nn_query",
 )
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdigs_b200.so")
+# DIGS_B200_LIB: measurement-only override (diagnostic builds with one piece of a kernel compiled out, csrc/Makefile DIAG=)
+LIB_PATH = os.environ.get("DIGS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdigs_b200.so")
 _lib = None
 
 

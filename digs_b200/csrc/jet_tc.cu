@@ -54,15 +54,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
     uint64_t* w_full = bars;                          // [STAGES]
     uint64_t* w_empty = bars + STAGES;                // [STAGES]
     uint64_t* b_ready = bars + 2 * STAGES;            // [2] epilogue -> MMA: operand rows of phase p complete (ETHREADS arrivals)
-    uint64_t* acc_ready = bars + 2 * STAGES + 2;      // MMA -> epilogue: accumulators of the step complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 3);
+    uint64_t* acc_ready = bars + 2 * STAGES + 2;      // [2] MMA -> epilogue: accumulators of the M tiles of phase p complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         mbar_init(&b_ready[0], G::ETHREADS);
         mbar_init(&b_ready[1], G::ETHREADS);
-        mbar_init(acc_ready, 1);
+        mbar_init(&acc_ready[0], 1);
+        mbar_init(&acc_ready[1], 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmapW);
     }
@@ -90,16 +91,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
             for (int64_t r = blockIdx.x; r < num_tiles; r += gridDim.x)
                 for (int j = 0; j < Lh; ++j) {
                     const int l = BWD ? (Lh - j) : (j + 1);
-                    for (int ks = 0; ks < G::KSLABS; ++ks)
-                        for (int m = 0; m < MT; ++m)
-                            for (int part = 0; part < G::NPARTS; ++part) {
-                                mbar_wait(&w_empty[stage], phase ^ 1);
-                                mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
-                                // rows: [dir = fwd|transposed][part = hi|lo][layer][H]
-                                tma_load_2d(sRing + stage * STAGE_BYTES, &tmapW, &w_full[stage], ks * 64,
-                                            (((BWD ? 2 : 0) + part) * Lh + (l - 1)) * H + m * 128);
-                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                            }
+                    auto load = [&](int ks, int m) {
+                        for (int part = 0; part < G::NPARTS; ++part) {
+                            mbar_wait(&w_empty[stage], phase ^ 1);
+                            mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
+                            // rows: [dir = fwd|transposed][part = hi|lo][layer][H]
+                            tma_load_2d(sRing + stage * STAGE_BYTES, &tmapW, &w_full[stage], ks * 64,
+                                        (((BWD ? 2 : 0) + part) * Lh + (l - 1)) * H + m * 128);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    };
+                    weight_tile_order<G>(load, [](int) {}, [](int) {});
                 }
         }
     } else if (warp == EPI_WARPS + 1) {
@@ -113,49 +115,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
             for (int64_t r = blockIdx.x; r < num_tiles; r += gridDim.x)
                 for (int j = 0; j < Lh; ++j) {
                     const uint32_t d_buf = tmem_base + ((j + 1) & 1) * G::ACC_COLS;
-                    for (int ks = 0; ks < G::KSLABS; ++ks) {
-                        if (ks % G::KS_PER_PH == 0) {
-                            mbar_wait(&b_ready[ks / G::KS_PER_PH], pb);
-                            tc_fence_after();
-                        }
-                        for (int m = 0; m < MT; ++m) {
-                            const uint32_t d_tmem = d_buf + m * N;
-                            mbar_wait(&w_full[stage], phase);   // A_hi tile: hi*hi (+ hi*lo)
-                            tc_fence_after();
-                            {
-                                const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
+                    auto issue = [&](int ks, int m) {
+                        const uint32_t d_tmem = d_buf + m * N;
+                        mbar_wait(&w_full[stage], phase);   // A_hi tile: hi*hi (+ hi*lo)
+                        tc_fence_after();
+                        {
+                            const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
 #pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) {
-                                    uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
-                                    uint32_t koff = (ks * 8 + kk * 2) * G::SK;
-                                    uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
-                                    umma_bf16(d_tmem, da, db, idesc, (ks | kk) != 0);
-                                    if constexpr (PASSES == 3) {
-                                        uint64_t dbl = make_smem_desc(sB_lo + koff, G::SN, G::SK, LAYOUT_SW128);
-                                        umma_bf16(d_tmem, da, dbl, idesc, 1);
-                                    }
+                            for (int kk = 0; kk < 4; ++kk) {
+                                uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
+                                uint32_t koff = (ks * 8 + kk * 2) * G::SK;
+                                uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
+                                umma_bf16(d_tmem, da, db, idesc, (ks | kk) != 0);
+                                if constexpr (PASSES == 3) {
+                                    uint64_t dbl = make_smem_desc(sB_lo + koff, G::SN, G::SK, LAYOUT_SW128);
+                                    umma_bf16(d_tmem, da, dbl, idesc, 1);
                                 }
+                            }
+                        }
+                        umma_commit(&w_empty[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if constexpr (PASSES == 3) {
+                            mbar_wait(&w_full[stage], phase);   // A_lo tile: lo*hi
+                            tc_fence_after();
+                            const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
+                                uint32_t koff = (ks * 8 + kk * 2) * G::SK;
+                                uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
+                                umma_bf16(d_tmem, da, db, idesc, 1);
                             }
                             umma_commit(&w_empty[stage]);
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                            if constexpr (PASSES == 3) {
-                                mbar_wait(&w_full[stage], phase);   // A_lo tile: lo*hi
-                                tc_fence_after();
-                                const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) {
-                                    uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
-                                    uint32_t koff = (ks * 8 + kk * 2) * G::SK;
-                                    uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
-                                    umma_bf16(d_tmem, da, db, idesc, 1);
-                                }
-                                umma_commit(&w_empty[stage]);
-                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                            }
                         }
-                    }
+                    };
+                    weight_tile_order<G>(issue,
+                                         [&](int ph) { mbar_wait(&b_ready[ph], pb); tc_fence_after(); },
+                                         [&](int ph) { umma_commit(&acc_ready[ph]); });
                     pb ^= 1;               // both phase barriers complete exactly once per operand-producing step
-                    umma_commit(acc_ready);
                 }
         }
     } else {
@@ -217,13 +215,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                                 pre[c][4 * h] = v.x; pre[c][4 * h + 1] = v.y; pre[c][4 * h + 2] = v.z; pre[c][4 * h + 3] = v.w;
                             }
                     };
-                    if (j > 0) {
-                        mbar_wait(acc_ready, pa);
-                        pa ^= 1;
-                        tc_fence_after();
-                    }
 #pragma unroll 1
                     for (int ph = 0; ph < NPH; ++ph) {
+                        if (j > 0) {      // the accumulators of this phase's M tiles (the MMA warp may still be filling the others)
+                            mbar_wait(&acc_ready[ph], pa);
+                            tc_fence_after();
+                        }
 #pragma unroll 1
                         for (int it = (wr + G::WQ - (ph * G::ROT) % G::WQ) % G::WQ; it < G::NITEMS; it += G::WQ) {
                             const int mt = ph * G::MTP + it / G::NGRP;
@@ -441,6 +438,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                             }
                         }
                     }
+                    if (j > 0) pa ^= 1;     // acc_ready[0..NPH) complete once per MMA step: one parity for both
                 }
             };
             if (full) run_tile(std::true_type{});

@@ -84,6 +84,31 @@ struct Cfg {
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
+// Order in which the weight tiles (K slab ks, M tile m) of one layer step are produced (TMA warp) and consumed (MMA warp):
+//   part 0: the K slabs of operand phase 0 for all M tiles                                    [after b_ready[0]]
+//   then, per M-tile half h: its M tiles over the K slabs of operand phase 1                   [after b_ready[1]]
+//   and the accumulators of half h are complete right after it -> ready(h): the epilogue of the next step starts on
+//   those M tiles while the tensor pipe is still working on the other half.
+template <class G, class Tile, class Wait, class Ready>
+__device__ __forceinline__ void weight_tile_order(Tile&& tile, Wait&& wait, Ready&& ready) {
+    if constexpr (G::NPH == 1) {
+        wait(0);
+        for (int ks = 0; ks < G::KSLABS; ++ks)
+            for (int m = 0; m < G::MT; ++m) tile(ks, m);
+        ready(0);
+    } else {
+        wait(0);
+        for (int ks = 0; ks < G::KS_PER_PH; ++ks)
+            for (int m = 0; m < G::MT; ++m) tile(ks, m);
+        wait(1);
+        for (int h = 0; h < 2; ++h) {
+            for (int m = h * G::MTP; m < (h + 1) * G::MTP; ++m)
+                for (int ks = G::KS_PER_PH; ks < G::KSLABS; ++ks) tile(ks, m);
+            ready(h);
+        }
+    }
+}
+
 // sin/cos of a phase of any magnitude: two-constant Cody-Waite reduction to [-pi, pi], then MUFU
 __device__ __forceinline__ void sincos_reduced(float t, float& s, float& c) {
     const float magic = 12582912.f;  // 1.5 * 2^23: round-to-nearest-integer trick

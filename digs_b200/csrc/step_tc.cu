@@ -105,8 +105,10 @@ struct SCfg {
 __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
 // ---- epilogue warps: one tile, both directions -------------------------------------------------------------------------
-template <int D, int LAP, int H, int PASSES>
-__device__ __forceinline__ void epi_tile(const StepArgs& a, const StepSeg& sg, const int64_t tl, uint8_t* smem,
+// SEG selects a.seg[SEG] statically: its fields are then constant-bank operands (a run-time index would turn every
+// access into an indexed constant load on the long scoreboard).
+template <int D, int LAP, int H, int PASSES, int SEG>
+__device__ __forceinline__ void epi_tile(const StepArgs& a, const int64_t tl, uint8_t* smem,
                                          const uint32_t tmem_base, uint64_t* b_ready, uint64_t* acc_ready, uint32_t& pa,
                                          float* planes_cta, const int n_acc, float* lsum) {
     using G = Cfg<D, LAP, H, PASSES>;
@@ -121,9 +123,9 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const StepSeg& sg, c
     float* sHead = reinterpret_cast<float*>(smem + S::OFF_HEAD);
     float* sAcc = reinterpret_cast<float*>(smem + S::OFF_ACC);
     const uint32_t usw = (uint32_t)(lane & 7) << 4;
+    const StepSeg& sg = a.seg[SEG];
     const int Lh = a.Lh;
     const int64_t p0 = tl * T;
-    const bool full = (p0 + T <= sg.n);
     const int64_t col_tile = sg.col0 + tl * (C * T);                  // first operand column of this tile
     const int64_t slot_stride = a.total_cols * (int64_t)H;            // words per layer slot of actP / GPw
 
@@ -146,13 +148,12 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const StepSeg& sg, c
             const uint32_t t_buf = tmem_base + ((uint32_t)(q * 32) << 16) + (j & 1) * G::ACC_COLS;
             float* pl_l = planes_cta + (int64_t)(l - 1) * (C * T * H);         // scratch slot of layer l (l >= 1)
             uint32_t* wd_l = (BWD ? a.GPw : a.actP) + (int64_t)(BWD ? (l - 1) : l) * slot_stride + col_tile * H;
-            if (j > 0) {
-                mbar_wait(acc_ready, pa);
-                pa ^= 1;
-                tc_fence_after();
-            }
 #pragma unroll 1
             for (int ph = 0; ph < NPH; ++ph) {
+                if (j > 0) {      // the accumulators of this phase's M tiles (the MMA warp may still be filling the others)
+                    mbar_wait(&acc_ready[ph], pa);
+                    tc_fence_after();
+                }
 #pragma unroll 1
                 for (int it = (wr + G::WQ - (ph * G::ROT) % G::WQ) % G::WQ; it < G::NITEMS; it += G::WQ) {
                     const int mt = ph * G::MTP + it / G::NGRP;
@@ -195,7 +196,11 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const StepSeg& sg, c
                     } else {
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
+#ifdef DIGS_DIAG_NO_PLANES
+                            const float4 v = make_float4(0.1f, 0.2f, 0.3f, 0.4f);
+#else
                             const float4 v = __ldcg(reinterpret_cast<const float4*>(pl_l + c * (T * H) + poff));   // written by this CTA: L2, not L1
+#endif
                             pre[c][0] = v.x; pre[c][1] = v.y; pre[c][2] = v.z; pre[c][3] = v.w;
                         }
                     }
@@ -265,9 +270,11 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const StepSeg& sg, c
                         for (int v = 0; v < P2; ++v) part[v] = (v < C * GP) ? out[v / GP][v % GP] * wl_u : 0.f;
                         warp_reduce_scatter<P2>(part, lane);
                         if (lane < C * GP) sHead[ub * N + (lane / GP) * T + g * GP + (lane % GP)] = part[0];
+#ifndef DIGS_DIAG_NO_PLANES
 #pragma unroll
                         for (int c = 0; c < C; ++c)
                             *reinterpret_cast<float4*>(pl_l + c * (T * H) + poff) = make_float4(pre[c][0], pre[c][1], pre[c][2], pre[c][3]);
+#endif
                     } else {
                         if (BWD) {
 #pragma unroll
@@ -293,22 +300,27 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const StepSeg& sg, c
                             mbar_arrive(&b_ready[ph]);
                         }
                         // (3) forward: this layer's pre-activations to the L2-resident scratch (layer 0 is recomputed)
+#ifndef DIGS_DIAG_NO_PLANES
                         if (!BWD && j > 0) {
 #pragma unroll
                             for (int c = 0; c < C; ++c)
                                 *reinterpret_cast<float4*>(pl_l + c * (T * H) + poff) = make_float4(pre[c][0], pre[c][1], pre[c][2], pre[c][3]);
                         }
+#endif
                         // (4) weight-gradient operand words (hi | lo << 16), tile-major columns; streamed (evict-first)
+#ifndef DIGS_DIAG_NO_WORDS      // diagnostic builds (make DIAG=NO_WORDS): timing only, results are wrong
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
                             uint32_t* dst = wd_l + (c * T + g * GP) * H + u;
 #pragma unroll
                             for (int i = 0; i < GP; ++i) {
                                 uint32_t w = __byte_perm(hiw[c][i >> 1], low[c][i >> 1], (i & 1) ? 0x7632 : 0x5410);
-                                if (!BWD && !full && pg + i >= sg.n) w = 0;      // padding columns contribute exact zeros
+                                // padding points (>= n) need no masking: their head adjoints are exact zeros (sUbar), so
+                                // every adjoint word of such a column is 0 and the finite layer-input words drop out
                                 __stcs(dst + i * H, w);
                             }
                         }
+#endif
                     }
                     // ---------------- per-unit parameter gradients of this item ---------------------------------------
                     if (BWD) {
@@ -334,6 +346,7 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const StepSeg& sg, c
                     }
                 }
             }
+            if (j > 0) pa ^= 1;     // acc_ready[0..NPH) complete once per MMA step: one parity for both
         }
     };
 
@@ -491,8 +504,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_step(const __grid_constant__
     uint64_t* w_full = bars;
     uint64_t* w_empty = bars + STAGES;
     uint64_t* b_ready = bars + 2 * STAGES;
-    uint64_t* acc_ready = bars + 2 * STAGES + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 3);
+    uint64_t* acc_ready = bars + 2 * STAGES + 2;      // [2]: accumulators of the M tiles of phase p complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     float* sLoss = reinterpret_cast<float*>(smem + S::OFF_LOSS);
     float* sAcc = reinterpret_cast<float*>(smem + S::OFF_ACC);
 
@@ -501,7 +514,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_step(const __grid_constant__
         for (int i = 0; i < STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         mbar_init(&b_ready[0], G::ETHREADS);
         mbar_init(&b_ready[1], G::ETHREADS);
-        mbar_init(acc_ready, 1);
+        mbar_init(&acc_ready[0], 1);
+        mbar_init(&acc_ready[1], 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmapW);
     }
@@ -526,15 +540,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_step(const __grid_constant__
                 for (int dir = 0; dir < 2; ++dir)
                     for (int j = 0; j < Lh; ++j) {
                         const int l = dir ? (Lh - j) : (j + 1);
-                        for (int ks = 0; ks < G::KSLABS; ++ks)
-                            for (int m = 0; m < MT; ++m)
-                                for (int part = 0; part < G::NPARTS; ++part) {
-                                    mbar_wait(&w_empty[stage], phase ^ 1);
-                                    mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
-                                    tma_load_2d(sRing + stage * STAGE_BYTES, &tmapW, &w_full[stage], ks * 64,
-                                                (((dir ? 2 : 0) + part) * Lh + (l - 1)) * H + m * 128);
-                                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                                }
+                        auto load = [&](int ks, int m) {
+                            for (int part = 0; part < G::NPARTS; ++part) {
+                                mbar_wait(&w_empty[stage], phase ^ 1);
+                                mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
+                                tma_load_2d(sRing + stage * STAGE_BYTES, &tmapW, &w_full[stage], ks * 64,
+                                            (((dir ? 2 : 0) + part) * Lh + (l - 1)) * H + m * 128);
+                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            }
+                        };
+                        weight_tile_order<G>(load, [](int) {}, [](int) {});
                     }
         }
     } else if (warp == EPI_WARPS + 1) {
@@ -548,49 +563,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_step(const __grid_constant__
                 for (int dir = 0; dir < 2; ++dir)
                     for (int j = 0; j < Lh; ++j) {
                         const uint32_t d_buf = tmem_base + ((j + 1) & 1) * G::ACC_COLS;
-                        for (int ks = 0; ks < G::KSLABS; ++ks) {
-                            if (ks % G::KS_PER_PH == 0) {
-                                mbar_wait(&b_ready[ks / G::KS_PER_PH], pb);
-                                tc_fence_after();
+                        auto issue = [&](int ks, int m) {
+                            const uint32_t d_tmem = d_buf + m * N;
+                            mbar_wait(&w_full[stage], phase);
+                            tc_fence_after();
+                            {
+                                const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
+                                    uint32_t koff = (ks * 8 + kk * 2) * G::SK;
+                                    uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
+#ifndef DIGS_DIAG_NO_MMA
+                                    umma_bf16(d_tmem, da, db, idesc, (ks | kk) != 0);
+                                    if constexpr (PASSES == 3) {
+                                        uint64_t dbl = make_smem_desc(sB_lo + koff, G::SN, G::SK, LAYOUT_SW128);
+                                        umma_bf16(d_tmem, da, dbl, idesc, 1);
+                                    }
+#else
+                                    (void)da; (void)db; (void)d_tmem;
+#endif
+                                }
                             }
-                            for (int m = 0; m < MT; ++m) {
-                                const uint32_t d_tmem = d_buf + m * N;
+                            umma_commit(&w_empty[stage]);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            if constexpr (PASSES == 3) {
                                 mbar_wait(&w_full[stage], phase);
                                 tc_fence_after();
-                                {
-                                    const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
+                                const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
 #pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk) {
-                                        uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
-                                        uint32_t koff = (ks * 8 + kk * 2) * G::SK;
-                                        uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
-                                        umma_bf16(d_tmem, da, db, idesc, (ks | kk) != 0);
-                                        if constexpr (PASSES == 3) {
-                                            uint64_t dbl = make_smem_desc(sB_lo + koff, G::SN, G::SK, LAYOUT_SW128);
-                                            umma_bf16(d_tmem, da, dbl, idesc, 1);
-                                        }
-                                    }
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
+                                    uint32_t koff = (ks * 8 + kk * 2) * G::SK;
+                                    uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
+#ifndef DIGS_DIAG_NO_MMA
+                                    umma_bf16(d_tmem, da, db, idesc, 1);
+#else
+                                    (void)da; (void)db;
+#endif
                                 }
                                 umma_commit(&w_empty[stage]);
                                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                                if constexpr (PASSES == 3) {
-                                    mbar_wait(&w_full[stage], phase);
-                                    tc_fence_after();
-                                    const uint32_t sA = smem_u32(sRing + stage * STAGE_BYTES);
-#pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk) {
-                                        uint64_t da = make_smem_desc(sA + kk * 32, 16, 1024, LAYOUT_SW128);
-                                        uint32_t koff = (ks * 8 + kk * 2) * G::SK;
-                                        uint64_t db = make_smem_desc(sB_hi + koff, G::SN, G::SK, LAYOUT_SW128);
-                                        umma_bf16(d_tmem, da, db, idesc, 1);
-                                    }
-                                    umma_commit(&w_empty[stage]);
-                                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                                }
                             }
-                        }
+                        };
+                        weight_tile_order<G>(issue,
+                                             [&](int ph) { mbar_wait(&b_ready[ph], pb); tc_fence_after(); },
+                                             [&](int ph) { umma_commit(&acc_ready[ph]); });
                         pb ^= 1;
-                        umma_commit(acc_ready);
                     }
         }
     } else {
@@ -599,13 +618,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_step(const __grid_constant__
         float* planes_cta = a.scratch + (int64_t)blockIdx.x * a.scratch_stride;
         float* lsum = sLoss;                                 // per-CTA sums: sdf, inter, eikonal, normal, div, sum of u_bar
         for (int64_t tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-            const int si = (tile >= a.seg[1].tile0) ? 1 : 0;
-            const StepSeg& sg = a.seg[si];
-            const int64_t tl = tile - sg.tile0;
-            if (sg.lap_chan)
-                epi_tile<D, 1, H, PASSES>(a, sg, tl, smem, tmem_base, b_ready, acc_ready, pa, planes_cta, n_acc, lsum);
+            // cloud 0 carries the Laplacian channel iff the loss has a divergence term; cloud 1 never does
+            if (tile >= a.seg[1].tile0)
+                epi_tile<D, 0, H, PASSES, 1>(a, tile - a.seg[1].tile0, smem, tmem_base, b_ready, acc_ready, pa, planes_cta, n_acc, lsum);
+            else if (a.seg[0].lap_chan)
+                epi_tile<D, 1, H, PASSES, 0>(a, tile, smem, tmem_base, b_ready, acc_ready, pa, planes_cta, n_acc, lsum);
             else
-                epi_tile<D, 0, H, PASSES>(a, sg, tl, smem, tmem_base, b_ready, acc_ready, pa, planes_cta, n_acc, lsum);
+                epi_tile<D, 0, H, PASSES, 0>(a, tile, smem, tmem_base, b_ready, acc_ready, pa, planes_cta, n_acc, lsum);
         }
         if (tid == 0) {
             // terms: [0] loss [1] sdf [2] inter [3] eikonal [4] normal [5] div (same slots as k_loss)
