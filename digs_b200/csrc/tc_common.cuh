@@ -66,6 +66,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst_smem, const void* tmap, ui
         : "memory");
 }
 
+// bulk tensor store shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src_smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tmap), "r"(smem_u32(src_smem)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- TMEM --------------------------------------------------------------------------------------
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {  // one full warp
@@ -153,11 +163,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // ---- bf16 hi/lo split -----------------------------------------------------------------------------
 // hi = bf16(x) (round to nearest), lo = bf16(x - hi): x ~ hi + lo to ~16 mantissa bits.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    float2 hf = __bfloat1622float2(h);
-    __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<uint32_t*>(&h);
-    lo = *reinterpret_cast<uint32_t*>(&l);
+    // cvt.rn.bf16x2.f32 d, hi_src, lo_src: the FIRST source lands in the upper half.  The two bf16 values are widened back
+    // with one shift / one mask (the compiler's __bfloat1622float2 spends two byte permutes and a re-pack on it).
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float ha = __uint_as_float(hi << 16);
+    const float hb = __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
 }
 
 __device__ __forceinline__ uint32_t elect_one() {

@@ -21,7 +21,7 @@ ride in its trailing slots through the all-reduce, so sharded runs report the gl
 import torch
 import torch.distributed as dist
 
-from .dist import FlatGrads
+from .dist import FlatGrads, gather_latent_grads
 from .jet import bump_param_epoch
 from .step import fused_step, fused_step_supported
 
@@ -89,6 +89,11 @@ class GraphedStep:
         self.launches_per_step = int(_lib.lib().digs_launch_count() - before)   # library kernels recorded in the graph
         self.loss_dict = {k: v.detach() for k, v in self.loss_dict.items()}
 
+    def release(self):
+        """Drop the captured graph.  Call this (or delete the object) BEFORE torch.distributed.destroy_process_group():
+        tearing the NCCL communicator down while a graph that captured its kernels is alive blocks forever."""
+        self.graph = None
+
     def _push_weights(self):
         w = list(self.criterion.weights) + [0.0] * 6
         if self.criterion.loss_type == "siren_wo_n":
@@ -117,8 +122,8 @@ class GraphedStep:
                     latent = self.latent_table.detach().index_select(0, self.indices)      # train_shapespace.py:122
                 loss_dict, _, lat_grad = fused_step(self.net, crit, self.mnfld, self.nonmnfld, self.normals, latent=latent)
                 if self.autodecoder:
-                    self.latent_grad.zero_()
-                    self.latent_grad.index_add_(0, self.indices, lat_grad)
+                    # rows of all ranks' shapes -> the dense table gradient every rank updates identically
+                    gather_latent_grads(self.latent_grad, self.indices, lat_grad, group=self.group)
             else:
                 m = self.mnfld.detach().requires_grad_()
                 nm = self.nonmnfld.detach().requires_grad_()
@@ -132,8 +137,6 @@ class GraphedStep:
                 ex[i:i + 1].copy_(loss_dict[k].detach().reshape(-1)[:1])
             if self.world > 1:
                 dist.all_reduce(self.flat.flat, op=dist.ReduceOp.SUM, group=self.group)
-                if self.autodecoder:
-                    dist.all_reduce(self.latent_grad, op=dist.ReduceOp.SUM, group=self.group)
             if self.optimizer is not None:
                 self.optimizer.step()
             return {k: ex[i] for i, k in enumerate(keys)}

@@ -127,12 +127,15 @@ def fused_step(net, criterion, mnfld_points, nonmnfld_points, mnfld_n_gt, latent
         grads[1].add_(sbg.sum(0))
         latent_grad = sbg @ lin0.weight.detach()[:, d:]
         if net.encoder_type == "autodecoder":
-            nrm_l = lat.norm(dim=-1)                                   # models/DiGS.py:48-49: mean over all points of ||latent||
-            latent_reg_term = nrm_l.mean()
+            # models/DiGS.py:48-49: mean over all points of ||latent|| = mean over the shapes of the GLOBAL batch (shapes
+            # sharded over ranks contribute partial sums that the gradient all-reduce adds up)
+            bs_glob = bs if gc is None else max(int(gc[1]) // max(n_n, 1), 1)
+            nrm_l = lat.norm(dim=-1)
+            latent_reg_term = nrm_l.sum() / bs_glob
             w5 = float(w[5])
             loss = loss + w5 * latent_reg_term                        # models/losses.py:183-184
-            latent_grad = latent_grad + (w5 / bs) * torch.where(nrm_l[:, None] > 0, lat / nrm_l[:, None].clamp_min(1e-30),
-                                                                torch.zeros_like(lat))
+            latent_grad = latent_grad + (w5 / bs_glob) * torch.where(nrm_l[:, None] > 0, lat / nrm_l[:, None].clamp_min(1e-30),
+                                                                     torch.zeros_like(lat))
             latent_rows = lat[:, None, :].expand(bs, n_n, lat.shape[1])
     div_loss = terms[5] if criterion.use_div else zero
     loss_dict = {"loss": loss, "sdf_term": terms[1], "inter_term": terms[2], "latent_reg_term": latent_reg_term,

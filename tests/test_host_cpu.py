@@ -215,6 +215,20 @@ fg.allreduce()
 ref = pts.mean(dim=(0, 1))
 assert torch.allclose(fg.flat[:3], ref, atol=1e-5), (fg.flat[:3], ref)
 assert int(fg.extra[0]) == 11
+# shapes sharded over ranks (SURVEY 8e row 3): the batch's shape indices split contiguously, and the (index, gradient row)
+# pairs of all ranks scattered into the dense latent-table gradient every rank then holds (duplicates in a batch add up)
+batch = torch.tensor([7, 2, 7, 5])
+mine = dd.shard_shapes(batch, rank, world)
+assert mine.tolist() == batch[2 * rank:2 * rank + 2].tolist()
+rows = torch.stack([torch.full((3,), 10.0 * rank + i) for i in range(2)])
+dense = torch.ones(9, 3)
+dd.gather_latent_grads(dense, mine, rows)
+ref = torch.zeros(9, 3)
+ref[7] = 0.0 + 10.0          # rank 0 row 0 (value 0) + rank 1 row 0 (value 10)
+ref[2] = 1.0
+ref[5] = 11.0
+assert torch.equal(dense, ref), dense
+assert [dd.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
 dist.destroy_process_group()
 print("ok", rank)
 '''
