@@ -11,6 +11,8 @@ models/losses.py and utils/utils.py (imported with five stub modules, oracle/ref
                 forward + DiGSLoss + backward, in fp64 (ground truth) and fp32 (the reference's own noise floor)
   * grid_*      get_3d_grid axes and decoder values in the reference's flat point order
   * divw_*      update_div_weight schedules
+  * trained_c2  weights after 200 iterations of the reference's own training loop on a synthetic torus + one step on them
+  * c1_training_curves  loss curves / fit metrics of the reference's 2-D sanity loop over three seeds (statistical parity)
 """
 import copy
 import hashlib
@@ -154,11 +156,13 @@ def make_inputs(case, dtype):
     return m, nrm, nm, lat
 
 
-def run_reference_step(ref_digs, case, dtype):
+def run_reference_step(ref_digs, case, dtype, state_dict=None, inputs=None):
     torch.manual_seed(case["seed"])
     net = ref_digs.DiGSNetwork(**case["net"])
+    if state_dict is not None:
+        net.load_state_dict(state_dict)
     crit = ref_digs.DiGSLoss(**copy.deepcopy(case["loss"]))
-    m, nrm, nm, lat = make_inputs(case, dtype)
+    m, nrm, nm, lat = make_inputs(case, dtype) if inputs is None else inputs
     net = net.to(dtype)
     m_t, n_t, nm_t = (torch.tensor(a, dtype=dtype) for a in (m, nrm, nm))
     m_t.requires_grad_()
@@ -190,12 +194,118 @@ def run_reference_step(ref_digs, case, dtype):
     return res, shas, (m, nrm, nm, lat)
 
 
+# ---- trained weights (SURVEY 7.3-1 / 8d "second data point"): where f ~ 0 the max-norm-relative error of f is worst ------
+TRAINED = dict(steps=200, n_batch=4096, n_eval=600, lr=5e-5, clip=10.0, decay=(1e2, 0.2, 1e2, 0.4, 0.0, 0.0))
+
+
+def reference_training_loop(ref_digs, net, crit, batches, lr, clip, decay, dtype=torch.float32):
+    """The reference's own iteration (train_surface_reconstruction.py:114-158 / train_basic_shape.py:94-135):
+    forward, DiGSLoss, backward, [clip_grad_norm_ 10], Adam.step, update_div_weight.  Returns the list of losses."""
+    opt = torch.optim.Adam(net.parameters(), lr=lr)
+    n_iter = len(batches)
+    losses = []
+    for it, (m, nrm, nm) in enumerate(batches):
+        m = torch.as_tensor(m, dtype=dtype).requires_grad_()
+        nm = torch.as_tensor(nm, dtype=dtype).requires_grad_()
+        net.zero_grad()
+        out = net(nm, m)
+        ld, _ = crit(out, m, nm, torch.as_tensor(nrm, dtype=dtype))
+        ld["loss"].backward()
+        if clip:
+            torch.nn.utils.clip_grad_norm_(net.parameters(), clip)
+        opt.step()
+        if decay is not None:
+            crit.update_div_weight(it, n_iter, decay)
+        losses.append(float(ld["loss"].detach()))
+    return losses
+
+
+def make_trained(ref_digs):
+    from digs_b200 import synth                     # analytic clouds only (numpy)
+    case = STEP_CASES["c2_small"]
+    cloud, normals = synth.surface_cloud(100000, "torus", seed=0)
+    batches = [synth.sample_batch(cloud, normals, TRAINED["n_batch"], seed=1000 + i, box=1.1) for i in range(TRAINED["steps"])]
+    torch.manual_seed(case["seed"])
+    net = ref_digs.DiGSNetwork(**case["net"])
+    crit = ref_digs.DiGSLoss(**copy.deepcopy(case["loss"]))
+    losses = reference_training_loop(ref_digs, net, crit, batches, TRAINED["lr"], TRAINED["clip"], TRAINED["decay"])
+    state = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    m, nrm, nm = synth.sample_batch(cloud, normals, TRAINED["n_eval"], seed=77, box=1.1)
+    inputs = (m, nrm, nm, None)
+    r64, _, _ = run_reference_step(ref_digs, case, torch.float64, state_dict=state, inputs=inputs)
+    r32, _, _ = run_reference_step(ref_digs, case, torch.float32, state_dict=state, inputs=inputs)
+    blob = dict(in_mnfld=m, in_normals=nrm, in_nonmnfld=nm, train_losses=np.array(losses))
+    for k, v in state.items():
+        blob["w_" + k] = v.numpy()
+    for k, v in r64.items():
+        blob["ref64_" + k] = v.astype(np.float32) if k.startswith("grad_") else v
+    for k, v in r32.items():
+        if not k.startswith("grad_"):
+            blob["ref32_" + k] = v
+    np.savez_compressed(os.path.join(OUT, "trained_c2.npz"), **blob)
+    print("trained_c2: loss %.3f -> %.3f after %d reference steps; |f_m| mean %.2e" % (
+        losses[0], losses[-1], len(losses), float(np.abs(r64["f_m"]).mean())))
+
+
+# ---- statistical N-step run on config 1 (SURVEY 4): loss curves of the reference's own 2-D sanity loop, several seeds ------
+CURVES = dict(steps=300, n_batch=2048, seeds=(11, 12, 13), lr=1e-4)      # sc_args.py:29 lr; train_basic_shape.py does not clip
+
+
+def c1_batches(seed, steps, n):
+    rng = np.random.RandomState(seed)
+    out = []
+    for _ in range(steps):
+        t = rng.uniform(0, 2 * np.pi, n)
+        nrm = np.stack([np.cos(t), np.sin(t)], 1).astype(np.float32)
+        out.append(((0.5 * nrm)[None], nrm[None], rng.uniform(-1.2, 1.2, size=(1, n, 2)).astype(np.float32)))
+    return out
+
+
+def c1_eval_points():
+    t = np.linspace(0, 2 * np.pi, 512, endpoint=False)
+    on = 0.5 * np.stack([np.cos(t), np.sin(t)], 1)
+    g = np.linspace(-1.0, 1.0, 33)
+    off = np.stack(np.meshgrid(g, g), -1).reshape(-1, 2)
+    return on.astype(np.float32), off.astype(np.float32)
+
+
+def make_curves(ref_digs):
+    case = STEP_CASES["c1_small"]
+    blob = dict(seeds=np.array(CURVES["seeds"]))
+    on, off = c1_eval_points()
+    for seed in CURVES["seeds"]:
+        torch.manual_seed(seed)
+        net = ref_digs.DiGSNetwork(**case["net"])
+        crit = ref_digs.DiGSLoss(**copy.deepcopy(case["loss"]))
+        losses = reference_training_loop(ref_digs, net, crit, c1_batches(seed, CURVES["steps"], CURVES["n_batch"]),
+                                         CURVES["lr"], None, (1e2, 0.2, 1e2, 0.4, 0.0, 0.0))
+        with torch.no_grad():
+            f_on = net.decoder(torch.tensor(on)).numpy()[:, 0]
+            f_off = net.decoder(torch.tensor(off)).numpy()[:, 0]
+        blob["loss_%d" % seed] = np.array(losses)
+        blob["f_on_abs_mean_%d" % seed] = np.array(np.abs(f_on).mean())
+        # agreement of the learnt field with the true signed distance of the r = 0.5 circle on a coarse grid
+        sdf = np.linalg.norm(off, axis=1) - 0.5
+        blob["sdf_err_%d" % seed] = np.array(np.abs(f_off - sdf).mean())
+        print("curves seed %d: loss %.2f -> %.2f, mean|f| on the circle %.3e, mean |f - sdf| %.3e" % (
+            seed, losses[0], np.mean(losses[-20:]), np.abs(f_on).mean(), np.abs(f_off - sdf).mean()))
+    np.savez_compressed(os.path.join(OUT, "c1_training_curves.npz"), **blob)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref_digs, ref_losses, ref_utils = reference_loader.load()
     if "--only-lossvar" in sys.argv:          # regenerate just the loss-variant fixtures
         make_lossvar(ref_digs)
         return
+    if "--only-trained" in sys.argv:
+        make_trained(ref_digs)
+        return
+    if "--only-curves" in sys.argv:
+        make_curves(ref_digs)
+        return
+    make_trained(ref_digs)
+    make_curves(ref_digs)
     make_lossvar(ref_digs)
 
     # ---- init fingerprints -----------------------------------------------------------------------

@@ -26,14 +26,15 @@ GRAD_TOL = 2e-4
 MODES = ["fp32", "bf16x2", "bf16"]
 # Stated bounds per precision mode (max-norm-relative vs the fp64 reference run): (jets, parameter gradients).
 #   fp32    CUDA-core fp32: the north-star 1e-4 bound.
-#   bf16x2  tcgen05, bf16 hi+lo split operands, 3 passes (~16 mantissa bits per operand): 5e-4 / 1e-3.
+#   bf16x2  tcgen05, bf16 hi+lo split operands, 3 passes (~16 mantissa bits per operand): 2.5e-4 / 3e-4, i.e. about twice
+#           what profiles/r02_error_table.md measures on the benchmark configuration (jets 1.1e-4, gradients <= 1.7e-4).
 #   bf16    tcgen05, single-pass bf16 operands: jets 5e-2; a fast preview mode, NOT a parity mode -- loss terms
 #           (exp(-100|f|)) and parameter gradients amplify its error, so only the jets are bounded for it.
-TOL = {"fp32": (JET_TOL, GRAD_TOL), "bf16x2": (5e-4, 1e-3), "bf16": (5e-2, None)}
+TOL = {"fp32": (JET_TOL, GRAD_TOL), "bf16x2": (2.5e-4, 3e-4), "bf16": (5e-2, None)}
 # Where the sqrt head's u -> 0 makes 1/sqrt|u| amplify rounding, every finite-precision evaluation (the reference's fp32 run
 # included) leaves the absolute bounds above; there the bound is a multiple of the fp32 noise floor measured on the very
-# same points (same closed form / same autograd evaluated in float32): 2x for fp32 mode, 10x for the bf16 hi+lo split.
-NOISE_MULT = {"fp32": 2.0, "bf16x2": 10.0}
+# same points (same closed form / same autograd evaluated in float32): 2x for fp32 mode, 3x for the bf16 hi+lo split.
+NOISE_MULT = {"fp32": 2.0, "bf16x2": 3.0}
 
 
 def _run_step(name, precision):
@@ -680,3 +681,107 @@ def test_cta_pair_kernel_passes_the_same_parity_cases():
                        env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(here))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+def _load_trained(net, g):
+    sd = {k[2:]: torch.tensor(g[k]) for k in g.files if k.startswith("w_")}
+    net.load_state_dict(sd)
+
+
+@pytest.mark.parametrize("path", ["two_call", "fused"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x2"])
+def test_step_on_trained_weights_matches_reference_fixture(precision, path):
+    """Second data point of SURVEY 7.3-1 / 8d: weights after 200 iterations of the reference's own training loop (synthetic
+    torus, C2 recipe).  f is close to zero on the surface there, so its max-norm-relative error is the worst case."""
+    from digs_b200.step import fused_step
+    if path == "fused" and precision == "fp32":
+        pytest.skip("the fused step covers the tensor-core modes")
+    case = STEP_CASES["c2_small"]
+    g = golden("trained_c2.npz")
+    net = build_net(case["net"], case["seed"], precision=precision).to(DEV)
+    _load_trained(net, g)
+    crit = digs_b200.DiGSLoss(**copy.deepcopy(case["loss"]))
+    m = torch.tensor(g["in_mnfld"], device=DEV)
+    nm = torch.tensor(g["in_nonmnfld"], device=DEV)
+    nrm = torch.tensor(g["in_normals"], device=DEV)
+    if path == "fused":
+        loss_dict, out, _ = fused_step(net, crit, m, nm, nrm)
+    else:
+        m.requires_grad_()
+        nm.requires_grad_()
+        out = net(nm, m)
+        loss_dict, _ = crit(out, m, nm, nrm)
+        loss_dict["loss"].backward()
+    JET, GRAD = TOL[precision]
+    errs = {}
+    for key, ref in (("manifold_pnts_pred", "f_m"), ("nonmanifold_pnts_pred", "f_n"), ("manifold_pnts_grad", "g_m"),
+                     ("nonmanifold_pnts_grad", "g_n"), ("nonmanifold_pnts_div", "lap_n")):
+        e, e32 = maxrel(out[key].detach().cpu(), g["ref64_" + ref]), maxrel(g["ref32_" + ref], g["ref64_" + ref])
+        errs[ref] = (e, e32)
+        assert e < max(JET, NOISE_MULT[precision] * e32), (ref, e, e32)
+    print("trained weights, %s/%s: (ours, reference fp32) vs fp64: %s" % (precision, path, {k: "%.1e/%.1e" % v for k, v in errs.items()}))
+    for key in ("loss", "sdf_term", "inter_term", "eikonal_term", "normals_loss", "div_loss"):
+        ref = float(g["ref64_term_" + key][0])
+        assert abs(float(loss_dict[key].detach().reshape(-1)[0]) - ref) <= JET * max(abs(ref), 1e-3), key
+    for pname, p in net.named_parameters():
+        assert maxrel(p.grad.cpu(), g["ref64_grad_" + pname]) < GRAD, pname
+
+
+def test_autodecoder_value_path_uses_each_shapes_latent():
+    """bs = 2 clouds with different latents under no_grad: every cloud is evaluated with its own latent, and a
+    direct decoder(points_with_latent) call whose rows mix latents uses each row's own (models/DiGS.py:142-151)."""
+    case = STEP_CASES["latent_small"]
+    g = golden("step_latent_small.npz")
+    net = build_net(case["net"], case["seed"], precision="fp32").to(DEV)
+    m = torch.tensor(g["in_mnfld"], device=DEV)
+    nm = torch.tensor(g["in_nonmnfld"], device=DEV)
+    lat = torch.tensor(g["in_latent"], device=DEV)
+    m_in = torch.cat([m, lat[:, None, :].expand(-1, m.shape[1], -1)], dim=-1)
+    nm_in = torch.cat([nm, lat[:, None, :].expand(-1, nm.shape[1], -1)], dim=-1)
+    with torch.no_grad():
+        out = net(nm_in, m_in)
+        mixed = net.decoder(nm_in.reshape(-1, nm_in.shape[-1]))[:, 0].reshape(nm.shape[:2])
+    assert maxrel(out["manifold_pnts_pred"].cpu(), g["ref64_f_m"]) < JET_TOL
+    assert maxrel(out["nonmanifold_pnts_pred"].cpu(), g["ref64_f_n"]) < JET_TOL
+    assert maxrel(mixed.cpu(), g["ref64_f_n"]) < JET_TOL
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x2"])
+def test_c1_training_run_is_statistically_the_reference(precision):
+    """an N-step training run on config 1 judged statistically.  300 iterations of the reference's 2-D
+    sanity loop (train_basic_shape.py:94-135: Adam 1e-4, no clipping, div-weight schedule) on the same batches, three
+    seeds; the reference's own fp32 / fp64 runs diverge weight-wise within a few steps, so the loss level
+    and the quality of the learnt field are compared, not the weights."""
+    from oracle.make_golden import CURVES, c1_batches, c1_eval_points
+    case = STEP_CASES["c1_small"]
+    g = golden("c1_training_curves.npz")
+    on, off = c1_eval_points()
+    sdf = np.linalg.norm(off, axis=1) - 0.5
+    ratios = []
+    for seed in CURVES["seeds"]:
+        net = build_net(case["net"], seed, precision=precision).to(DEV)
+        crit = digs_b200.DiGSLoss(**copy.deepcopy(case["loss"]))
+        opt = torch.optim.Adam(net.parameters(), lr=CURVES["lr"])
+        batches = c1_batches(seed, CURVES["steps"], CURVES["n_batch"])
+        losses = []
+        for it, (m, nrm, nm) in enumerate(batches):
+            m = torch.tensor(m, device=DEV).requires_grad_()
+            nm = torch.tensor(nm, device=DEV).requires_grad_()
+            opt.zero_grad()
+            ld, _ = crit(net(nm, m), m, nm, torch.tensor(nrm, device=DEV))
+            ld["loss"].backward()
+            opt.step()
+            crit.update_div_weight(it, len(batches), (1e2, 0.2, 1e2, 0.4, 0.0, 0.0))
+            losses.append(float(ld["loss"].detach()))
+        ref = g["loss_%d" % seed]
+        assert abs(losses[0] - ref[0]) < 1e-3 * abs(ref[0])                      # identical start (same init, same batch)
+        ours_end, ref_end = float(np.mean(losses[-30:])), float(np.mean(ref[-30:]))
+        with torch.no_grad():
+            f_off = net.decoder(torch.tensor(off, device=DEV))[:, 0].cpu().numpy()
+        sdf_err = float(np.abs(f_off - sdf).mean())
+        print("seed %d %s: end loss %.2f (reference %.2f), mean |f - sdf| %.3f (reference %.3f)" % (
+            seed, precision, ours_end, ref_end, sdf_err, float(g["sdf_err_%d" % seed])))
+        ratios.append(ours_end / ref_end)
+        assert 0.6 < ours_end / ref_end < 1.6, (seed, ours_end, ref_end)
+        assert sdf_err < 1.5 * float(g["sdf_err_%d" % seed]) + 0.02
+    assert 0.8 < float(np.mean(ratios)) < 1.25, ratios

@@ -124,3 +124,22 @@ def test_grid_values_port():
     pts = torch.tensor(g["cube16/points_f16"].astype(np.float32))
     v = ref_autograd.grid_values(params, pts, head_of(net)).numpy()
     assert maxrel(v, g["cube16/values32"]) < 1e-5
+
+
+def test_closed_form_oracle_on_trained_weights():
+    """The oracle is pinned on weights after 200 reference training iterations too (tests/golden/trained_c2.npz)."""
+    g = golden("trained_c2.npz")
+    n_layers = len([k for k in g.files if k.startswith("w_") and k.endswith("weight")])
+    params = [(g["w_decoder.fc_block.net.%d.0.weight" % i].astype(np.float64),
+               g["w_decoder.fc_block.net.%d.0.bias" % i].astype(np.float64)) for i in range(n_layers)]
+    case = STEP_CASES["c2_small"]
+    res = jet_spec.step(params, g["in_mnfld"][0].astype(np.float64), g["in_nonmnfld"][0].astype(np.float64),
+                        g["in_normals"][0].astype(np.float64), (1.6, 0.1), case["loss"]["weights"],
+                        case["loss"]["loss_type"], case["loss"]["div_type"], case["loss"]["div_clamp"])
+    assert maxrel(res["fn"]["f"], g["ref64_f_n"][0]) < 1e-9
+    assert maxrel(res["fn"]["grad"], g["ref64_g_n"][0]) < 1e-9
+    assert maxrel(res["fn"]["lap"], g["ref64_lap_n"][0]) < 1e-9
+    assert abs(res["terms"]["loss"] - float(g["ref64_term_loss"][0])) < 1e-9 * abs(float(g["ref64_term_loss"][0]))
+    for i, (dW, db) in enumerate(res["grads"]):
+        assert maxrel(dW, g["ref64_grad_decoder.fc_block.net.%d.0.weight" % i]) < 1e-6     # fixture gradients are stored in fp32
+        assert maxrel(db, g["ref64_grad_decoder.fc_block.net.%d.0.bias" % i]) < 1e-6
