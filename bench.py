@@ -419,8 +419,9 @@ def accuracy_of_mode(args, dev):
     errs = {"f": rel(out["nonmanifold_pnts_pred"].detach().cpu()[0], ref["fn"]["f"]),
             "grad_f": rel(out["nonmanifold_pnts_grad"].detach().cpu()[0], ref["fn"]["grad"]),
             "lap_f": rel(out["nonmanifold_pnts_div"].detach().cpu()[0], ref["fn"]["lap"]),
-            "param_grads_worst": max(max(rel(lins[i].weight.grad.cpu(), ref["grads"][i][0]),
-                                         rel(lins[i].bias.grad.cpu(), ref["grads"][i][1])) for i in range(len(lins)))}
+            "param_grads": {("dW%d" % i): rel(lins[i].weight.grad.cpu(), ref["grads"][i][0]) for i in range(len(lins))}}
+    errs["param_grads"].update({("db%d" % i): rel(lins[i].bias.grad.cpu(), ref["grads"][i][1]) for i in range(len(lins))})
+    errs["param_grads_worst"] = max(errs["param_grads"].values())
     errs["what"] = "max-norm-relative error vs the fp64 oracle, 2048+2048 points of the benchmark workload, mode %s" % args.mode
     return errs
 

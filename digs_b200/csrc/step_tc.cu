@@ -81,6 +81,12 @@ struct StepArgs {
     int acc_smem;
 };
 
+// Two experiments on this kernel that did NOT pay (profiles/r02_experiments.md):
+//  * register redistribution with setmaxnreg (20 warps, helpers 32 / epilogue 112 registers -- the pool is the launch-time
+//    allocation, 5 x 96 per scheduler, so 4 x 112 + 32 is the most that fits; 120 / 32 and 112 / 56 never get their
+//    allocation and hang): spills gone, tile kernel 0.690 ms against 0.675 ms without it;
+//  * a compact run-time loop over the weight-tile order in the MMA / TMA warps instead of the unrolled callbacks:
+//    the issue thread's index arithmetic sits on the critical path (0.732 ms, grid query 228 ms instead of 204 ms).
 template <int D, int H_, int PASSES>
 struct SCfg {
     using G1 = Cfg<D, 1, H_, PASSES>;

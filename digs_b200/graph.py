@@ -120,26 +120,33 @@ class GraphedStep:
                 latent = None
                 if self.autodecoder:
                     latent = self.latent_table.detach().index_select(0, self.indices)      # train_shapespace.py:122
-                loss_dict, _, lat_grad = fused_step(self.net, crit, self.mnfld, self.nonmnfld, self.normals, latent=latent)
+                # the kernel adds the loss scalars straight into the trailing slots of the flat gradient buffer (zeroed
+                # with it above): one collective carries gradients and loss terms, and no copy kernels are recorded
+                loss_dict, _, lat_grad = fused_step(self.net, crit, self.mnfld, self.nonmnfld, self.normals, latent=latent,
+                                                    terms=self.flat.extra)
                 if self.autodecoder:
                     # rows of all ranks' shapes -> the dense table gradient every rank updates identically
                     gather_latent_grads(self.latent_grad, self.indices, lat_grad, group=self.group)
+                ex = self.flat.extra
+                views = {"loss": ex[0], "sdf_term": ex[1], "inter_term": ex[2], "eikonal_term": ex[3], "normals_loss": ex[4],
+                         "div_loss": ex[5] if crit.use_div else torch.zeros((), device=ex.device),
+                         "latent_reg_term": ex[6], "curv_loss": ex[7]}
             else:
                 m = self.mnfld.detach().requires_grad_()
                 nm = self.nonmnfld.detach().requires_grad_()
                 out = self.net(nm, m)
                 loss_dict, _ = crit(out, m, nm, self.normals)
                 loss_dict["loss"].backward()
-            # the 8 scalars ride in the flat buffer's trailing slots (one collective for gradients and loss terms)
-            keys = ("loss", "sdf_term", "inter_term", "latent_reg_term", "eikonal_term", "normals_loss", "div_loss", "curv_loss")
-            ex = self.flat.extra
-            for i, k in enumerate(keys):
-                ex[i:i + 1].copy_(loss_dict[k].detach().reshape(-1)[:1])
+                keys = ("loss", "sdf_term", "inter_term", "eikonal_term", "normals_loss", "div_loss", "latent_reg_term", "curv_loss")
+                ex = self.flat.extra
+                for i, k in enumerate(keys):
+                    ex[i:i + 1].copy_(loss_dict[k].detach().reshape(-1)[:1])
+                views = {k: ex[i] for i, k in enumerate(keys)}
             if self.world > 1:
                 dist.all_reduce(self.flat.flat, op=dist.ReduceOp.SUM, group=self.group)
             if self.optimizer is not None:
                 self.optimizer.step()
-            return {k: ex[i] for i, k in enumerate(keys)}
+            return views
         finally:
             if had_dw is None:
                 if hasattr(crit, "device_weights"):

@@ -33,7 +33,7 @@ def fused_step_supported(net, criterion):
             and not net.compute_manifold_laplacian)
 
 
-def fused_step(net, criterion, mnfld_points, nonmnfld_points, mnfld_n_gt, latent=None, grads=None):
+def fused_step(net, criterion, mnfld_points, nonmnfld_points, mnfld_n_gt, latent=None, grads=None, terms=None):
     """Forward jets of both clouds + DiGSLoss + the reverse pass, accumulated into the parameter gradients.
 
     mnfld_points (bs, Nm, d), nonmnfld_points (bs, Nn, d), mnfld_n_gt (bs, Nm, d): float32 CUDA tensors (coordinates only).
@@ -41,6 +41,9 @@ def fused_step(net, criterion, mnfld_points, nonmnfld_points, mnfld_n_gt, latent
                 concatenates it to every point; here it folds into a per-shape bias of layer 0).
     grads       optional list of tensors aligned with net.decoder.fc_block.flat_params() to ACCUMULATE into
                 (default: each parameter's .grad, created as zeros when missing).
+    terms       optional ZEROED float32[8] device tensor the kernel adds the loss scalars into (slots: loss, sdf, inter,
+                eikonal, normal, div, -, -); GraphedStep passes the tail of its flat gradient buffer, so the scalars ride
+                through the gradient all-reduce without any copy kernel.
     Returns (loss_dict, output_pred, latent_grad): the 8 loss tensors of models/losses.py:186-188, the dict of
     models/DiGS.py:63-66 (+ the gradient / divergence keys of the drop-in network), and d loss / d latent (or None).
     """
@@ -89,7 +92,8 @@ def fused_step(net, criterion, mnfld_points, nonmnfld_points, mnfld_n_gt, latent
     l_n = torch.empty(bs * n_n, dtype=torch.float32, device=dev) if want_lap else None
     f_m = torch.empty(bs * n_m, dtype=torch.float32, device=dev)
     g_m = torch.empty(bs * n_m, d, dtype=torch.float32, device=dev)
-    terms = torch.zeros(8, dtype=torch.float32, device=dev)
+    if terms is None:
+        terms = torch.zeros(8, dtype=torch.float32, device=dev)
     if criterion.loss_type == "siren_wo_n":
         criterion.weights[2] = 0                                      # models/losses.py:153
     cfg = _lib.DigsLossCfg()
@@ -133,7 +137,9 @@ def fused_step(net, criterion, mnfld_points, nonmnfld_points, mnfld_n_gt, latent
             nrm_l = lat.norm(dim=-1)
             latent_reg_term = nrm_l.sum() / bs_glob
             w5 = float(w[5])
-            loss = loss + w5 * latent_reg_term                        # models/losses.py:183-184
+            terms[0:1].add_(w5 * latent_reg_term)                      # models/losses.py:183-184 (in place: `terms` may be shared)
+            terms[6:7].add_(latent_reg_term)
+            loss = terms[0]
             latent_grad = latent_grad + (w5 / bs_glob) * torch.where(nrm_l[:, None] > 0, lat / nrm_l[:, None].clamp_min(1e-30),
                                                                      torch.zeros_like(lat))
             latent_rows = lat[:, None, :].expand(bs, n_n, lat.shape[1])
