@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                             const int64_t pg = p0 + g * GP;              // first point of the group
                             const int goff = g * GP * H + u;             // word offset from the tile / layer base ([col][unit] words)
                             const int poff = g * GP * H + u * 4;         // plane offset ([point / 4][unit][point % 4] floats)
+                            DIGS_ASSERT(g < G::NGRP && mt < MT && u < H && (FULL || p0 < a.n_pad));
                             const uint32_t t_base = t_buf + mt * N;
                             float bsum = 0.f, wlsum = 0.f, w0s0 = 0.f, w0s1 = 0.f, w0s2 = 0.f;
                             float acc[C][GP];                             // TMEM values: fwd pre-activations, bwd incoming adjoint
@@ -458,6 +459,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                             for (int w = 0; w < G::NUB; ++w) s += sHead[w * N + c * T + e];
                             v[c] = s;
                         }
+                        DIGS_ASSERT(gp >= 0 && gp < a.n);
                         float uu = v[0] + __ldg(a.b_last);
                         if (a.head_saved) {
                             a.head_saved[gp * C] = uu;

@@ -3,6 +3,13 @@
 #include "digs_internal.h"
 #include "tc_common.cuh"
 
+#ifdef DIGS_DEBUG
+#include <cassert>
+#define DIGS_ASSERT(cond) assert(cond)      // make DEBUG=1: device-side bounds checks (compute-sanitizer is closed on the GPU pool)
+#else
+#define DIGS_ASSERT(cond) ((void)0)
+#endif
+
 namespace digs {
 namespace tcpath {
 

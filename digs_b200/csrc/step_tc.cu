@@ -168,6 +168,7 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const int64_t tl, ui
                     const int u = ub * 32 + lane;
                     const int64_t pg = p0 + g * GP;
                     const int poff = g * GP * H + u * 4;                  // plane offset ([point / 4][unit][point % 4])
+                    DIGS_ASSERT((int64_t)(Lh - 1) * (C * T * H) + (C - 1) * (T * H) + poff + 4 <= a.scratch_stride && g < G::NGRP && mt < G::MT);
                     const uint32_t t_base = t_buf + mt * N;
                     float bsum = 0.f, wlsum = 0.f, w0s0 = 0.f, w0s1 = 0.f, w0s2 = 0.f;
                     float acc[C][GP];
@@ -296,6 +297,7 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const int64_t tl, ui
                             split2(out[c][2], out[c][3], hiw[c][1], low[c][1]);
                             const uint32_t off = rowoff + (uint32_t)(ncol >> 6) * G::SN +
                                                  (((((uint32_t)ncol & 63) >> 3) << 4) ^ usw) + (uint32_t)(ncol & 4) * 2;
+                            DIGS_ASSERT(ncol + GP <= N && off + 8 <= (uint32_t)G::B_PART && u < H);
                             sts_v2(sB + off, hiw[c][0], hiw[c][1]);
                             if constexpr (PASSES == 3) sts_v2(sB + G::B_PART + off, low[c][0], low[c][1]);
                         }
@@ -318,6 +320,7 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const int64_t tl, ui
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
                             uint32_t* dst = wd_l + (c * T + g * GP) * H + u;
+                            DIGS_ASSERT(col_tile + c * T + g * GP + GP <= a.total_cols && (BWD ? l - 1 : l) >= 0 && (BWD ? l - 1 : l) < Lh);
 #pragma unroll
                             for (int i = 0; i < GP; ++i) {
                                 uint32_t w = __byte_perm(hiw[c][i >> 1], low[c][i >> 1], (i & 1) ? 0x7632 : 0x5410);
@@ -402,6 +405,7 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const int64_t tl, ui
                 }
                 if constexpr (LAP) lp = a.scale * (g1 * v[1 + D] + g2 * gg);
             }
+            DIGS_ASSERT(gp >= 0 && gp < sg.n);
             sg.f[gp] = f;
 #pragma unroll
             for (int k = 0; k < D; ++k) sg.grad[gp * D + k] = gr[k];
