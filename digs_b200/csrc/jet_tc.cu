@@ -171,30 +171,134 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
         const int64_t plane_stride = a.n_pad * (int64_t)H;     // one (layer, channel) plane of `planes` / actP / GP
         uint32_t* words = reinterpret_cast<uint32_t*>(BWD ? a.GP_words : a.actP);
 
-        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int64_t p0 = tile * T;
-            const bool full = (p0 + T <= a.n);     // no tail handling needed anywhere in this tile
-            // ---- stage the tile's coordinates (and head adjoints) ----------------------------------------------------
+        // ---- stage a tile's coordinates (and head adjoints) into coordinate buffer xb --------------------------------------
+        auto stage = [&](const int64_t tile, const int xb) {
+            const int64_t q0 = tile * T;
+            float* xs = sXyz + xb * (N * 3);
             for (int e = tid; e < T; e += G::ETHREADS) {
-                int64_t gp = p0 + e;
+                int64_t gp = q0 + e;
                 if (gp >= a.n) gp = a.n - 1;
                 float x, y, z;
                 point_coords(a.src, gp, x, y, z);
-                sXyz[e * 3] = x; sXyz[e * 3 + 1] = y; sXyz[e * 3 + 2] = z;
+                xs[e * 3] = x; xs[e * 3 + 1] = y; xs[e * 3 + 2] = z;
             }
             if constexpr (BWD) {
                 for (int e = tid; e < T * C; e += G::ETHREADS) {
-                    int64_t gp = p0 + e / C;
+                    int64_t gp = q0 + e / C;
                     sUbar[e] = (gp < a.n) ? __ldg(a.ubar + gp * C + (e % C)) : 0.f;
                 }
             }
             named_bar_sync(1, G::ETHREADS);
+        };
+
+        // ---- layer 0 of a tile on its own (forward direction): pre-activations from the coordinates, activation, operand for
+        // the first hidden layer.  Used to start the NEXT tile before the current tile's last-layer step (see the schedule below);
+        // the same arithmetic as step j = 0 of run_tile.
+        auto layer0 = [&](const int64_t tile, const int xb) {
+            const int64_t q0 = tile * T;
+            const float* xs = sXyz + xb * (N * 3);
+            uint32_t* wd0 = words ? words + q0 * H : nullptr;       // actP slot 0
+#pragma unroll 1
+            for (int ph = 0; ph < NPH; ++ph) {
+#pragma unroll 1
+                for (int it = (wr + G::WQ - (ph * G::ROT) % G::WQ) % G::WQ; it < G::NITEMS; it += G::WQ) {
+                    const int mt = ph * G::MTP + it / G::NGRP;
+                    const int g = it % G::NGRP;
+                    const int u = (mt * 4 + q) * 32 + lane;
+                    const int64_t pg = q0 + g * GP;
+                    const float4 w0v = __ldg(reinterpret_cast<const float4*>(a.w0_30) + u);
+                    float out[C][GP];
+#pragma unroll
+                    for (int i = 0; i < GP; ++i) {
+                        const float* xp = xs + (g * GP + i) * 3;
+                        float bz = w0v.w;
+                        if (a.src.shape_bias) {
+                            int64_t gp = pg + i < a.n ? pg + i : a.n - 1;
+                            bz = 30.f * __ldg(a.src.shape_bias + (gp / a.src.pps) * H + u);
+                        }
+                        float s, c;
+                        sincos_reduced(fmaf(w0v.z, xp[2], fmaf(w0v.y, xp[1], fmaf(w0v.x, xp[0], bz))), s, c);
+                        out[0][i] = s;
+                        if constexpr (D > 0) {
+                            out[1][i] = c * w0v.x;
+                            if constexpr (D > 1) out[2][i] = c * w0v.y;
+                            if constexpr (D > 2) out[3][i] = c * w0v.z;
+                            float S2 = w0v.x * w0v.x;
+                            if constexpr (D > 1) S2 = fmaf(w0v.y, w0v.y, S2);
+                            if constexpr (D > 2) S2 = fmaf(w0v.z, w0v.z, S2);
+                            if constexpr (LAP) out[C - 1][i] = -s * S2;
+                        }
+                    }
+                    const uint32_t rowoff = (uint32_t)(u >> 3) * G::SK + (uint32_t)(u & 7) * 128;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int ncol = c * T + g * GP;
+                        uint32_t hiw[GP / 2], low[GP / 2];
+#pragma unroll
+                        for (int i = 0; i < GP / 2; ++i) split2(out[c][2 * i], out[c][2 * i + 1], hiw[i], low[i]);
+                        if constexpr (GP >= 8) {
+#pragma unroll
+                            for (int h = 0; h < GP / 8; ++h) {
+                                const int nc = ncol + 8 * h;
+                                const uint32_t off = rowoff + (uint32_t)(nc >> 6) * G::SN + (((((uint32_t)nc & 63) >> 3) << 4) ^ usw);
+                                sts_v4(sB + off, hiw[4 * h], hiw[4 * h + 1], hiw[4 * h + 2], hiw[4 * h + 3]);
+                                if constexpr (PASSES == 3) sts_v4(sB + G::B_PART + off, low[4 * h], low[4 * h + 1], low[4 * h + 2], low[4 * h + 3]);
+                            }
+                        } else {
+                            const uint32_t off = rowoff + (uint32_t)(ncol >> 6) * G::SN +
+                                                 (((((uint32_t)ncol & 63) >> 3) << 4) ^ usw) + (uint32_t)(ncol & 4) * 2;
+                            sts_v2(sB + off, hiw[0], hiw[1]);
+                            if constexpr (PASSES == 3) sts_v2(sB + G::B_PART + off, low[0], low[1]);
+                        }
+                        if (wd0) {      // wgrad operand words of layer 1's input; padding points are exact zeros
+                            uint32_t* dst = wd0 + c * plane_stride + g * GP * H + u;
+#pragma unroll
+                            for (int i = 0; i < GP; ++i) {
+                                uint32_t w = __byte_perm(hiw[i >> 1], low[i >> 1], (i & 1) ? 0x7632 : 0x5410);
+                                if (pg + i >= a.n) w = 0;
+                                if (pg + i < a.n_pad) dst[i * H] = w;
+                            }
+                        }
+                    }
+                    if (it + G::WQ >= G::NITEMS) {
+                        fence_proxy_async();
+                        tc_fence_before();
+                        mbar_arrive(&b_ready[ph]);
+                    }
+                }
+            }
+        };
+
+        // Forward kernels with an even number of MMA steps per tile run layer 0 of the NEXT tile before the last-layer step of
+        // the current one: that step and the head use no tensor core, so the MMA warp works on the next tile's first hidden
+        // layer meanwhile (into the other TMEM buffer; the operand buffer is free once all accumulators of the tile are complete).
+        const bool pipe = !BWD && ((Lh & 1) == 0);
+        bool layer0_done = false;      // layer 0 of the tile about to start has been run already
+        int xb = 0;
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int64_t p0 = tile * T;
+            const bool full = (p0 + T <= a.n);     // no tail handling needed anywhere in this tile
+            const float* xs = sXyz + xb * (N * 3);
+            const int j_start = layer0_done ? 1 : 0;
+            if (!layer0_done) stage(tile, xb);
+            const int64_t nxt = tile + gridDim.x;
+            const bool pipe_next = pipe && nxt < num_tiles;
 
             auto run_tile = [&](auto full_tag) {
                 constexpr bool FULL = decltype(full_tag)::value;
-                for (int j = 0; j <= Lh; ++j) {
+                for (int j = j_start; j <= Lh; ++j) {
                     const int l = BWD ? (Lh - j) : j;          // layer whose (pre-)activations this step touches
                     const bool last = (j == Lh);
+                    bool awaited = false;
+                    if (!BWD && last && pipe_next) {
+                        // every MMA of this tile has to be complete before the next tile's layer 0 rewrites the operand
+#pragma unroll 1
+                        for (int ph = 0; ph < NPH; ++ph) mbar_wait(&acc_ready[ph], pa);
+                        tc_fence_after();
+                        stage(nxt, xb ^ 1);
+                        layer0(nxt, xb ^ 1);
+                        awaited = true;
+                    }
                     const uint32_t t_buf = tmem_base + ((uint32_t)(q * 32) << 16) + (j & 1) * G::ACC_COLS;
                     // layer slot bases: planes slot = l-1 (both directions); GP slot = l-1 (reverse), actP slot = l (forward)
                     float* pl_l = a.planes ? a.planes + (int64_t)(l - 1) * C * plane_stride + p0 * H : nullptr;
@@ -217,7 +321,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                     };
 #pragma unroll 1
                     for (int ph = 0; ph < NPH; ++ph) {
-                        if (j > 0) {      // the accumulators of this phase's M tiles (the MMA warp may still be filling the others)
+                        if (j > 0 && !awaited) {   // the accumulators of this phase's M tiles (the MMA warp may still be filling the others)
                             mbar_wait(&acc_ready[ph], pa);
                             tc_fence_after();
                         }
@@ -248,7 +352,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                                 const float4 w0v = __ldg(reinterpret_cast<const float4*>(a.w0_30) + u);
 #pragma unroll
                                 for (int i = 0; i < GP; ++i) {
-                                    const float* xp = sXyz + (g * GP + i) * 3;
+                                    const float* xp = xs + (g * GP + i) * 3;
                                     float bz = w0v.w;
                                     if (a.src.shape_bias) {
                                         int64_t gp = pg + i < a.n ? pg + i : a.n - 1;
@@ -325,7 +429,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                                 // layer-0 parameter gradients: dW0[u][k] += 30 (zhat x_k + Zhat_k), db0[u] += 30 zhat
 #pragma unroll
                                 for (int i = 0; i < GP; ++i) {
-                                    const float* xp = sXyz + (g * GP + i) * 3;
+                                    const float* xp = xs + (g * GP + i) * 3;
                                     bsum += out[0][i];
                                     if constexpr (D > 0) w0s0 += fmaf(out[0][i], xp[0], out[1][i]);
                                     if constexpr (D > 1) w0s1 += fmaf(out[0][i], xp[1], out[2][i]);
@@ -494,7 +598,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_net(const __grid_constant__ 
                     }
                 }
             }
-            named_bar_sync(1, G::ETHREADS);   // sXyz / sHead / sUbar are rewritten by the next tile
+            named_bar_sync(1, G::ETHREADS);   // sHead / sUbar are rewritten by the next tile
+            layer0_done = pipe_next;
+            if (pipe_next) xb ^= 1;
         }
         if (n_acc) {
             // every epilogue warp has passed the barrier above for its last tile: the CTA's sums are complete

@@ -79,8 +79,8 @@ struct Cfg {
     static constexpr int ETHREADS = EPI_WARPS * 32;
     static constexpr int NUB = H / 32;                // 32-unit blocks
     static constexpr int OFF_RING = B_BYTES;
-    static constexpr int OFF_XYZ = OFF_RING + STAGES * STAGE_BYTES;      // [N*3] floats
-    static constexpr int OFF_UBAR = OFF_XYZ + N * 3 * 4;                  // [N] floats
+    static constexpr int OFF_XYZ = OFF_RING + STAGES * STAGE_BYTES;      // [2][N*3] floats (the next tile's coordinates are staged early)
+    static constexpr int OFF_UBAR = OFF_XYZ + 2 * N * 3 * 4;              // [N] floats
     static constexpr int OFF_BAR = OFF_UBAR + N * 4;
     static constexpr int OFF_HEAD = OFF_BAR + 256;                        // forward: [NUB][N] floats of last-layer partial sums
     static constexpr int OFF_ACC = OFF_HEAD;                              // reverse: [(Lh+1) db | 3 dW0 | dw_last][H] floats (optional)

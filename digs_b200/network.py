@@ -245,8 +245,13 @@ class DiGSNetwork(nn.Module):
     """Same signature as models/DiGS.py:25-66."""
 
     def __init__(self, latent_size, in_dim=3, decoder_hidden_dim=256, nl="sine", encoder_type=None,
-                 decoder_n_hidden_layers=8, init_type="siren", sphere_init_params=[1.6, 1.0], precision="fp32"):
+                 decoder_n_hidden_layers=8, init_type="siren", sphere_init_params=[1.6, 1.0], precision=None):
         super().__init__()
+        if precision is None:       # callers written for the reference cannot pass it: DIGS_B200_PRECISION selects the mode
+            import os
+            precision = os.environ.get("DIGS_B200_PRECISION", "fp32")
+        if precision not in _lib.MODES:
+            raise ValueError("precision must be one of %s" % (sorted(_lib.MODES),))
         self.encoder_type = encoder_type
         self.init_type = init_type
         if encoder_type == "autodecoder":

@@ -5,7 +5,8 @@ The reference's ``utils/utils.py`` imports five packages that are not installed 
 touched by the hot path, so empty stub modules are enough.
 
 ``/root/reference`` exists only in the build container.  ``__graft_entry__.build()`` installs the three
-module directories the hot path touches (models/, utils/ -- unmodified) into the git-ignored
+module directories the hot path touches (models/, utils/, and surface_reconstruction/ whose training script serves as an
+integration harness -- all unmodified) into the git-ignored
 ``baseline/_ref/`` so that the *reference arm* of bench.py can time the real reference modules on the GPU
 box's host cores (and, for context, through stock PyTorch CUDA).  The -m gpu tests and smoke() never import
 it: they use the committed golden fixtures.
@@ -36,9 +37,9 @@ def install(dst=INSTALLED_ROOT, src="/root/reference"):
     import shutil
     if not os.path.isfile(os.path.join(src, "models", "DiGS.py")):
         return False
-    for sub in ("models", "utils"):
+    for sub in ("models", "utils", "surface_reconstruction"):      # the last one: the training script used as a harness
         shutil.copytree(os.path.join(src, sub), os.path.join(dst, sub), dirs_exist_ok=True,
-                        ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+                        ignore=shutil.ignore_patterns("__pycache__", "*.pyc", "scripts", "camera_params", "log"))
     for f in ("LICENCE", "README.md"):
         if os.path.isfile(os.path.join(src, f)):
             shutil.copy(os.path.join(src, f), os.path.join(dst, f))
