@@ -430,6 +430,43 @@ def accuracy_of_mode(args, dev):
     return errs
 
 
+def whole_iteration_leg(args, dev, iters=200):
+    """train_surface_reconstruction.py:114-158 as one CUDA-graph replay per iteration with zero host synchronisations:
+    DeviceSampler draws the batch from the HBM-resident cloud, digs_step_fused, global-norm clip + Adam (step count on the
+    device); the host only advances the div-weight schedule.  Timed over `iters` back-to-back iterations, one sync at the end."""
+    import digs_b200
+    from digs_b200 import synth
+    cfg = CONFIGS["c2"]
+    torch.manual_seed(MODEL_SEED)
+    net = digs_b200.DiGSNetwork(**cfg["net"], precision=args.mode).to(dev)
+    crit = digs_b200.DiGSLoss(**copy.deepcopy(cfg["loss"]))
+    cloud, normals = synth.surface_cloud(100000, "torus", seed=0)
+    sampler = digs_b200.DeviceSampler(torch.tensor(cloud, device=dev), torch.tensor(normals, device=dev), cfg["n_points"],
+                                      grid_range=cfg["box"], seed=0, device=dev)
+    opt = digs_b200.FusedClipAdam(net.parameters(), lr=5e-5, max_norm=10.0, device_step=True)
+    it = digs_b200.GraphedStep(net, crit, cfg["n_points"], cfg["n_points"], sampler=sampler, optimizer=opt)
+    for i in range(10):
+        it.step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(iters):
+        ld = it.step()
+        crit.update_div_weight(i, iters, (1e2, 0.2, 1e2, 0.4, 0.0, 0.0))
+    e1.record()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1) / iters
+    out = {"ms_per_iteration": ms, "value": 2 * cfg["n_points"] / (ms * 1e-3), "unit": "points/s",
+           "wall_ms_per_iteration": 1e3 * wall / iters, "iterations": iters, "gpu_launches": it.launches_per_step,
+           "final_loss": float(ld["loss"]),
+           "what": "sampling + forward + DiGSLoss + backward + clip_grad_norm_(10) + Adam as one CUDA graph replay per "
+                   "iteration; no host synchronisation inside the loop, div-weight schedule advanced on the host"}
+    it.release()
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     import digs_b200
@@ -570,6 +607,13 @@ def run_ours(args, rank, world, local_rank):
             except Exception as ex:       # an extra leg must never take the headline line down
                 extra[name] = {"error": "%s: %s" % (type(ex).__name__, ex)}
             torch.cuda.empty_cache()
+    # ---- the complete training iteration as ONE graph: on-device batch sampling -> fused step -> clip + Adam ---
+    if world == 1 and not args.no_extra and args.config == "c2":
+        try:
+            extra["whole_iteration_one_graph"] = whole_iteration_leg(args, dev)
+        except Exception as ex:
+            extra["whole_iteration_one_graph"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        torch.cuda.empty_cache()
     if rank == 0:
         if extra:
             line["extra_legs"] = extra

@@ -38,9 +38,10 @@ def main():
                                  div_type="l1", div_clamp=50)
     decay = (1e2, 0.2, 1e2, 0.4, 0.0, 0.0)
     if args.graph:
-        opt = DiGSNet.FusedClipAdam(net.parameters(), lr=5e-5, max_norm=10.0)
+        # the whole iteration -- [sampling,] forward, loss, backward, clip + Adam -- is ONE CUDA graph replay
+        opt = DiGSNet.FusedClipAdam(net.parameters(), lr=5e-5, max_norm=10.0, device_step=True)
         sampler = DiGSNet.DeviceSampler(cloud, normals, args.n_points, grid_range=1.1, seed=0) if args.device_sampler else None
-        step = DiGSNet.GraphedStep(net, criterion, args.n_points, args.n_points, flat=opt.flat_grads, sampler=sampler)
+        step = DiGSNet.GraphedStep(net, criterion, args.n_points, args.n_points, sampler=sampler, optimizer=opt)
     else:
         opt = torch.optim.Adam(net.parameters(), lr=5e-5, betas=(0.9, 0.999))
     t0 = time.time()
@@ -49,7 +50,6 @@ def main():
             m, nrm, nm = (torch.from_numpy(a).to(dev) for a in synth.sample_batch(cloud, normals, args.n_points, seed=it))
         if args.graph:
             loss_dict = step.step() if args.device_sampler else step.step(m, nm, nrm)
-            opt.step()
         else:
             m.requires_grad_()
             nm.requires_grad_()
