@@ -5,8 +5,10 @@ A "step" = forward jets of one 15 000 + 15 000 point batch (value + gradient on 
 off-surface cloud) + DiGSLoss + the reverse pass to all parameter gradients (+ the gradient all-reduce when N > 1),
 on the SRB recipe network (4x256 sine MLP, MFGI init, BASELINE.json configs[1]).
 
-    python bench.py --gpus 1 --steps 20 --warmup 5              # our arm
-    python bench.py --impl reference --steps 5 --warmup 2       # the reference algorithm on the host cores
+    python bench.py --gpus 1 --steps 20 --warmup 5              # our arm (one CUDA-graph replay per step)
+    python bench.py --impl reference --steps 5 --warmup 2       # the unmodified reference modules on the host cores
+    torchrun ... bench.py --gpus 8 --scaling strong             # one batch's points split over the ranks (default: weak)
+    python bench.py --config c4 | c5                            # scene (8x512) / shapespace (latent 256) workloads
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
 """
@@ -32,15 +34,6 @@ LOSS_KW = dict(weights=[3e3, 1e2, 1e2, 5e1, 1e2], loss_type="siren_wo_n_w_div", 
 MODEL_SEED = 3627473            # surface_recon_args.py:13
 N_POINTS = 15000                # run_surf_recon_exp.sh:53
 H, LH, D = 256, 4, 3
-# algorithmic GEMM FLOPs: forward C*2*Lh*H^2 per point; training = 3x
-FLOP_FWD_NONMNFLD = (2 + D) * 2 * LH * H * H
-FLOP_FWD_MNFLD = (1 + D) * 2 * LH * H * H
-FLOP_STEP = 3 * N_POINTS * (FLOP_FWD_NONMNFLD + FLOP_FWD_MNFLD)
-# dram__bytes_read.sum + dram__bytes_write.sum of the forward-jet kernel (C=5, 15000 points, saving for the reverse pass),
-# per launch, from the `ncu --set full` capture summarised in profiles/r01_full_tc_kernels.md.  The kernel's algorithmic
-# bytes are the saved planes + wgrad operand: 2 * 15000 * 4 layers * 5 channels * 256 units * 4 B = 614 MB.
-FWD_DRAM_BYTES = {"bf16x2": 559.65e6}
-FWD_SAVED_BYTES = N_POINTS * (LH * 5 * H * 8 + 5 * 4)      # C = 5 channels: fp32 planes + (hi|lo) words per layer, head per point
 
 
 def measured_peaks():

@@ -17,6 +17,12 @@ CONFIGS = [
     ("C5 decoder 8x256 mfgi (no latent)", dict(latent_size=0, in_dim=3, decoder_hidden_dim=256, nl="sine", encoder_type="none", decoder_n_hidden_layers=8, init_type="mfgi", sphere_init_params=[1.6, 0.1]), 6000, 1.2),
 ]
 W = [3e3, 1e2, 1e2, 5e1, 1e2]
+TRAINED = None
+_g = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "trained_c2.npz")
+if os.path.isfile(_g):
+    _z = np.load(_g)
+    TRAINED = {k[2:]: torch.tensor(_z[k]) for k in _z.files if k.startswith("w_")}
+    CONFIGS.insert(2, ("C2 trained weights (200 reference iterations, torus)", CONFIGS[1][1], 15000, 1.1))
 print("| configuration | points | mode | f | grad f | lap f | loss | max dW | max db |")
 print("|---|---:|---|---:|---:|---:|---:|---:|---:|")
 for name, kw, n, box in CONFIGS:
@@ -26,6 +32,12 @@ for name, kw, n, box in CONFIGS:
     m_np, nm_np = (0.5 * v).astype(np.float32), rng.uniform(-box, box, size=(n, d)).astype(np.float32)
     torch.manual_seed(3627473)
     base = digs_b200.DiGSNetwork(**kw)
+    if TRAINED is not None and name.startswith("C2 trained"):
+        base.load_state_dict(TRAINED)
+        from digs_b200 import synth
+        cloud, cn = synth.surface_cloud(100000, "torus", seed=0)
+        mb, nb, nmb = synth.sample_batch(cloud, cn, n, seed=5, box=box)
+        m_np, v, nm_np = mb[0], nb[0].astype(np.float64), nmb[0]
     head = tuple(base.decoder.fc_block.sphere_init_params) if kw["init_type"] != "siren" else None
     P64 = [(l.weight.detach().double().numpy(), l.bias.detach().double().numpy()) for l in base.decoder.fc_block.linears()]
     ref = jet_spec.step(P64, m_np.astype(np.float64), nm_np.astype(np.float64), v, head, W)
@@ -40,6 +52,8 @@ for name, kw, n, box in CONFIGS:
     for mode in ("fp32", "bf16x2", "bf16"):
         torch.manual_seed(3627473)
         net = digs_b200.DiGSNetwork(**kw, precision=mode).cuda()
+        if TRAINED is not None and name.startswith("C2 trained"):
+            net.load_state_dict(TRAINED)
         crit = digs_b200.DiGSLoss(copy.deepcopy(W), "siren_wo_n_w_div", "linear", "l1", 50)
         m = torch.tensor(m_np[None], device="cuda").requires_grad_(); nm = torch.tensor(nm_np[None], device="cuda").requires_grad_()
         out = net(nm, m)
@@ -49,3 +63,15 @@ for name, kw, n, box in CONFIGS:
                   lap=out["nonmanifold_pnts_div"][0].detach().cpu().numpy())
         grads = [(l.weight.grad.cpu().numpy(), l.bias.grad.cpu().numpy()) for l in net.decoder.fc_block.linears()]
         row(mode, fn, dict(loss=float(ld["loss"].detach())), grads)
+        if mode != "fp32":       # the same step through digs_step_fused (tile kernel + weight-gradient GEMM)
+            torch.manual_seed(3627473)
+            net = digs_b200.DiGSNetwork(**kw, precision=mode).cuda()
+            if TRAINED is not None and name.startswith("C2 trained"):
+                net.load_state_dict(TRAINED)
+            crit = digs_b200.DiGSLoss(copy.deepcopy(W), "siren_wo_n_w_div", "linear", "l1", 50)
+            ld, out, _ = digs_b200.fused_step(net, crit, torch.tensor(m_np[None], device="cuda"), torch.tensor(nm_np[None], device="cuda"),
+                                              torch.tensor(v[None].astype(np.float32), device="cuda"))
+            fn = dict(f=out["nonmanifold_pnts_pred"][0].cpu().numpy(), grad=out["nonmanifold_pnts_grad"][0].cpu().numpy(),
+                      lap=out["nonmanifold_pnts_div"][0].cpu().numpy())
+            grads = [(l.weight.grad.cpu().numpy(), l.bias.grad.cpu().numpy()) for l in net.decoder.fc_block.linears()]
+            row(mode + " (fused step)", fn, dict(loss=float(ld["loss"])), grads)
