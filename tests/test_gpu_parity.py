@@ -703,15 +703,18 @@ def test_device_sampler_distribution():
 
 
 def test_cta_pair_kernel_passes_the_same_parity_cases():
-    """The opt-in CTA-pair (cta_group::2) variant of the jet kernel (csrc/jet_tc_pair.cu, DIGS_B200_PAIR=1) must stay
-    bit-for-tolerance equivalent: the fixture, full-size and ragged-cloud cases re-run in a child process with the switch
-    set (the library reads it once per process)."""
+    """The CTA-pair (cta_group::2) variant of the jet kernel (csrc/jet_tc_pair.cu) is not part of the default build
+    (`make PAIR=1 OUT=<lib>`); when DIGS_TEST_PAIR_LIB names such a library the fixture, full-size and ragged-cloud cases are
+    re-run on it in a child process (DIGS_B200_LIB + DIGS_B200_PAIR=1; the library reads the switch once per process)."""
     import os
     import subprocess
     import sys
+    lib = os.environ.get("DIGS_TEST_PAIR_LIB")
+    if not lib or not os.path.isfile(lib):
+        pytest.skip("no PAIR=1 build given (DIGS_TEST_PAIR_LIB)")
     if os.environ.get("DIGS_B200_PAIR") == "1":
         pytest.skip("already inside the paired run")
-    env = dict(os.environ, DIGS_B200_PAIR="1")
+    env = dict(os.environ, DIGS_B200_PAIR="1", DIGS_B200_LIB=lib)
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-x", "-q", "-m", "gpu", "-k",
                         "test_step_matches_reference_fixture or test_full_size_c2 or edge or grid"],
