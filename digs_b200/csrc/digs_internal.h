@@ -88,8 +88,24 @@ int step_fused(const DigsNet* net, const float* nonmnfld, int64_t nn, const floa
                int64_t xyz_stride, const float* sb_n, const float* sb_m, int64_t pps_n, int64_t pps_m, int want_lap,
                const DigsLossCfg* cfg, float* f_n, float* g_n, float* lap_n, float* f_m, float* g_m, float* terms,
                const DigsGrads* grads, float* sbg_n, float* sbg_m, void* ws, int passes, cudaStream_t st);
+// Tile-round completion counters of the fused step: lets the weight-gradient GEMM start (programmatic dependent launch)
+// on the SMs whose tile-kernel CTA has already exited, while the other CTAs still work on the last round of tiles.
+constexpr int WG_MAX_ROUNDS = 1023;             // ctr[0 .. rounds): tiles finished per round; ctr[WG_MAX_ROUNDS]: CTAs done
+constexpr int WG_QUEUE_IDX = WG_MAX_ROUNDS - 1; // ctr[WG_QUEUE_IDX]: next work unit of the weight-gradient GEMM (rounds use [0, WG_QUEUE_IDX))
+#ifdef DIGS_DIAG_TRACE                          // make DIAG=TRACE: globaltimer stamps of both grids behind the counters (scripts/overlap_trace.py)
+constexpr size_t WG_CTR_BYTES = (WG_MAX_ROUNDS + 1) * sizeof(unsigned int) + 8192 * 8;
+#else
+constexpr size_t WG_CTR_BYTES = (WG_MAX_ROUNDS + 1) * sizeof(unsigned int);
+#endif
+struct WgradSync {
+    unsigned int* ctr;        // NULL: plain launch, no flags
+    int grid;                 // CTAs of the tile kernel (tile t belongs to round t / grid)
+    int64_t total_tiles;
+    int64_t tiles0, cols0;    // cloud 0: tiles, operand columns
+    int ct0, ct1;             // operand columns per tile of cloud 0 / cloud 1
+};
 int wgrad(const DigsNet* net, const __nv_bfloat16* GP_words, const __nv_bfloat16* actP, int C, int64_t n_pad,
-          const DigsGrads* grads, int passes, cudaStream_t st);
+          const DigsGrads* grads, int passes, cudaStream_t st, const WgradSync* sync = nullptr);
 }  // namespace tcpath
 
 // ---- fused loss (loss_fused.cu) -------------------------------------------------------------

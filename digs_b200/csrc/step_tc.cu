@@ -79,6 +79,7 @@ struct StepArgs {
     float* dw_last;
     float* db_last;
     int acc_smem;
+    unsigned int* round_ctr;    // NULL or WgradSync counters: [round] += 1 per finished tile, [WG_MAX_ROUNDS] += 1 per finished CTA
 };
 
 // Two experiments on this kernel that did NOT pay (profiles/r02_experiments.md):
@@ -107,6 +108,14 @@ struct SCfg {
     static_assert(G0::N == G1::N && G0::B_BYTES == G1::B_BYTES && G0::TMEM_COLS == G1::TMEM_COLS, "clouds must share the operand tile");
     static_assert(G0::GP == 4 && G1::GP == 4, "jet tiles use 4-point groups");
 };
+
+// L2 load that the compiler must leave where it is written (the plane prefetch of the NEXT item belongs at the end of the
+// current one: hoisted, its 4 x C registers would stay live across the whole item and spill)
+__device__ __forceinline__ float4 ldcg_pinned(const float* p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
@@ -148,6 +157,20 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const int64_t tl, ui
 
     auto run_pass = [&](auto bwd_tag) {
         constexpr bool BWD = decltype(bwd_tag)::value;
+#ifndef DIGS_DIAG_NO_PREFETCH
+        // Reverse direction: the stored planes of an item do not depend on the accumulators.  They are fetched from L2 one item
+        // ahead -- at the end of the item before it in this warp's program order, across phase and layer boundaries -- so the
+        // L2 latency runs under the wait for the tensor pipe instead of after it.  Every load is unconditional (clamped to a
+        // valid address when there is no next item): a conditionally defined array would be demoted to local memory.
+        float4 pv[C];
+        auto fetch_planes = [&](int ln, int phn, int itn) {
+            const int mtn = phn * G::MTP + itn / G::NGRP, gn = itn % G::NGRP;
+            const float* src = planes_cta + (int64_t)(ln >= 1 ? ln - 1 : 0) * (C * T * H) + gn * GP * H + ((mtn * 4 + q) * 32 + lane) * 4;
+#pragma unroll
+            for (int c = 0; c < C; ++c) pv[c] = ldcg_pinned(src + c * (T * H));
+        };
+        if (BWD) fetch_planes(Lh, 0, wr % G::WQ);
+#endif
         for (int j = 0; j <= Lh; ++j) {
             const int l = BWD ? (Lh - j) : j;
             const bool last = (j == Lh);
@@ -156,12 +179,13 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const int64_t tl, ui
             uint32_t* wd_l = (BWD ? a.GPw : a.actP) + (int64_t)(BWD ? (l - 1) : l) * slot_stride + col_tile * H;
 #pragma unroll 1
             for (int ph = 0; ph < NPH; ++ph) {
+                const int it_first = (wr + G::WQ - (ph * G::ROT) % G::WQ) % G::WQ;
                 if (j > 0) {      // the accumulators of this phase's M tiles (the MMA warp may still be filling the others)
                     mbar_wait(&acc_ready[ph], pa);
                     tc_fence_after();
                 }
 #pragma unroll 1
-                for (int it = (wr + G::WQ - (ph * G::ROT) % G::WQ) % G::WQ; it < G::NITEMS; it += G::WQ) {
+                for (int it = it_first; it < G::NITEMS; it += G::WQ) {
                     const int mt = ph * G::MTP + it / G::NGRP;
                     const int g = it % G::NGRP;
                     const int ub = mt * 4 + q;
@@ -205,6 +229,8 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const int64_t tl, ui
                         for (int c = 0; c < C; ++c) {
 #ifdef DIGS_DIAG_NO_PLANES
                             const float4 v = make_float4(0.1f, 0.2f, 0.3f, 0.4f);
+#elif !defined(DIGS_DIAG_NO_PREFETCH)
+                            const float4 v = pv[c];
 #else
                             const float4 v = __ldcg(reinterpret_cast<const float4*>(pl_l + c * (T * H) + poff));   // written by this CTA: L2, not L1
 #endif
@@ -353,6 +379,16 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const int64_t tl, ui
                             }
                         }
                     }
+#ifndef DIGS_DIAG_NO_PREFETCH
+                    if (BWD) {      // this warp's next item: same phase, else the first item of the next phase / layer step
+                        int itn = it + G::WQ, phn = ph, ln = l;
+                        if (itn >= G::NITEMS) {
+                            if (++phn == NPH) { phn = 0; --ln; }
+                            itn = (wr + G::WQ - (phn * G::ROT) % G::WQ) % G::WQ;
+                        }
+                        fetch_planes(ln, phn, itn);
+                    }
+#endif
                 }
             }
             if (j > 0) pa ^= 1;     // acc_ready[0..NPH) complete once per MMA step: one parity for both
@@ -540,6 +576,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_step(const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int Lh = a.Lh;
+    // the weight-gradient GEMM is a programmatic dependent launch: its CTAs may be dispatched as soon as SMs free up (they
+    // synchronise on round_ctr, not on the completion of this grid)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#ifdef DIGS_DIAG_TRACE
+    if (a.round_ctr && tid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        reinterpret_cast<unsigned long long*>(a.round_ctr + WG_MAX_ROUNDS + 1)[256 + blockIdx.x] = t;
+    }
+#endif
 
     if (warp == EPI_WARPS) {
         // ================= TMA producer: per tile the forward weights (layers 1..Lh), then the transposed ones (Lh..1) ==
@@ -635,6 +681,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_step(const __grid_constant__
                 epi_tile<D, 1, H, PASSES, 0>(a, tile, smem, tmem_base, b_ready, acc_ready, pa, planes_cta, n_acc, lsum);
             else
                 epi_tile<D, 0, H, PASSES, 0>(a, tile, smem, tmem_base, b_ready, acc_ready, pa, planes_cta, n_acc, lsum);
+            // every epilogue thread has issued the tile's operand words (barrier at the end of epi_tile): publish the tile
+            if (a.round_ctr && tid == 0) {
+                __threadfence();
+                atomicAdd(a.round_ctr + tile / gridDim.x, 1u);
+            }
         }
         if (tid == 0) {
             // terms: [0] loss [1] sdf [2] inter [3] eikonal [4] normal [5] div (same slots as k_loss)
@@ -668,7 +719,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_step(const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
+    if (a.round_ctr && tid == 0) {      // the per-unit gradients and loss sums of this CTA are out as well
+        __threadfence();
+        atomicAdd(a.round_ctr + WG_MAX_ROUNDS, 1u);
+    }
     if (warp == EPI_WARPS + 1) tmem_dealloc<G::TMEM_COLS>(tmem_base);
+#ifdef DIGS_DIAG_TRACE
+    if (a.round_ctr && tid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        reinterpret_cast<unsigned long long*>(a.round_ctr + WG_MAX_ROUNDS + 1)[blockIdx.x] = t;
+    }
+#endif
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------------
@@ -705,7 +767,7 @@ static StepLayout step_layout(const DigsNet* net, int64_t nn, int64_t nm, int wa
 
 size_t step_ws_bytes(const DigsNet* net, int64_t nn, int64_t nm, int want_lap) {
     StepLayout L = step_layout(net, nn, nm, want_lap);
-    return prep_ws_bytes(net) + 2 * L.words_bytes + L.scratch_bytes;
+    return prep_ws_bytes(net) + 2 * L.words_bytes + L.scratch_bytes + WG_CTR_BYTES;
 }
 
 template <int D, int H, int PASSES>
@@ -758,6 +820,16 @@ int step_fused(const DigsNet* net, const float* nonmnfld, int64_t nn, const floa
     a.GPw = reinterpret_cast<uint32_t*>(w + prep_ws_bytes(net) + L.words_bytes);
     a.scratch = reinterpret_cast<float*>(w + prep_ws_bytes(net) + 2 * L.words_bytes);
     a.scratch_stride = (int64_t)L.scratch_stride;
+    // tile-round counters for the overlapped weight-gradient GEMM (DIGS_B200_WGRAD_OVERLAP=0: plain stream order)
+    const int grid_ctas = (int)(L.total_tiles < num_sms() ? L.total_tiles : num_sms());
+    bool overlap = (L.total_tiles + grid_ctas - 1) / grid_ctas <= WG_QUEUE_IDX;
+    if (const char* e = getenv("DIGS_B200_WGRAD_OVERLAP")) overlap = overlap && e[0] != '0';
+    if (const char* e = getenv("DIGS_B200_STEP_NO_WGRAD")) overlap = overlap && e[0] != '1';
+    if (overlap) {
+        a.round_ctr = reinterpret_cast<unsigned int*>(w + prep_ws_bytes(net) + 2 * L.words_bytes + L.scratch_bytes);
+        cudaError_t me = cudaMemsetAsync(a.round_ctr, 0, WG_CTR_BYTES, st);
+        if (me != cudaSuccess) { set_error("tc step: counter reset: %s", cudaGetErrorString(me)); return DIGS_ECUDA; }
+    }
     a.total_tiles = L.total_tiles;
     a.total_cols = L.total_cols;
     const float* xyz[2] = {nonmnfld, mnfld};
@@ -826,8 +898,16 @@ int step_fused(const DigsNet* net, const float* nonmnfld, int64_t nn, const floa
         if (e[0] == '1') return DIGS_OK;
     }
     // one weight-gradient GEMM over the columns of both clouds (tile-major columns: C = 1, n_pad = total_cols)
+    WgradSync sync{};
+    sync.ctr = a.round_ctr;
+    sync.grid = grid_ctas;
+    sync.total_tiles = L.total_tiles;
+    sync.tiles0 = L.tiles[0];
+    sync.cols0 = L.cols[0];
+    sync.ct0 = L.C[0] * L.T[0];
+    sync.ct1 = L.C[1] * L.T[1];
     return wgrad(net, reinterpret_cast<const __nv_bfloat16*>(a.GPw), reinterpret_cast<const __nv_bfloat16*>(a.actP), 1,
-                 L.total_cols, grads, passes, st);
+                 L.total_cols, grads, passes, st, &sync);
 }
 
 }  // namespace tcpath

@@ -204,3 +204,67 @@ class GraphedStep:
         if self.optimizer is not None:
             bump_param_epoch()      # the replayed optimizer wrote the parameters: cached operand copies are stale for eager calls
         return self.loss_dict
+
+    # ---- pipelined host feed ---------------------------------------------------------------------------------------------
+    # The reference feeds its loop from DataLoader workers (train_surface_reconstruction.py:44-46, 114-119: the batch of
+    # iteration i+1 is prepared while iteration i runs) and reads the loss for logging.  submit() / result() are that loop
+    # shape without a host synchronisation per iteration: the host-to-device copy of batch i+1 runs on a copy stream while
+    # the graph of iteration i executes, and the loss of iteration i is read back asynchronously and handed out one call
+    # later.  Every iteration still pays its own copy in and its own read out.
+    def _pipe_init(self):
+        dev = self._inputs.device
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._stage = [torch.empty_like(self._inputs) for _ in range(2)]
+        self._stage_full = [torch.cuda.Event() for _ in range(2)]
+        self._stage_free = [None, None]
+        self._loss_host = torch.zeros(4, 8, dtype=torch.float32).pin_memory()
+        self._loss_done = [torch.cuda.Event() for _ in range(4)]
+        self._ticket = 0
+
+    @torch.no_grad()
+    def submit(self, packed_host, indices=None):
+        """Queues one iteration on a pinned host batch in pack_host_batch layout (the `packed` tensor it returned) and
+        returns a ticket for result().  Does not wait for the device; at most two iterations are in flight (result() of
+        ticket t must be taken before submit() number t + 3 reuses its read-back slot)."""
+        if self.sampler is not None:
+            raise RuntimeError("GraphedStep.submit: this graph draws its batch on the device (sampler=); call step()")
+        if not hasattr(self, "_copy_stream"):
+            self._pipe_init()
+        if (packed_host.is_cuda or not packed_host.is_pinned() or packed_host.dtype != torch.float32
+                or packed_host.numel() != self._inputs.numel()):
+            raise ValueError("GraphedStep.submit: needs the pinned float32 tensor of pack_host_batch()")
+        if [p.data_ptr() for p in self.net.parameters()] != self._param_ptrs:
+            raise RuntimeError("digs_b200.GraphedStep: parameter storage moved since capture")
+        t = self._ticket
+        k = t & 1
+        main = torch.cuda.current_stream(self._inputs.device)
+        with torch.cuda.stream(self._copy_stream):
+            if self._stage_free[k] is not None:
+                self._copy_stream.wait_event(self._stage_free[k])      # the iteration that used this buffer has consumed it
+            self._stage[k].copy_(packed_host.view(-1), non_blocking=True)
+            self._stage_full[k].record(self._copy_stream)
+        main.wait_event(self._stage_full[k])
+        self._inputs.copy_(self._stage[k], non_blocking=True)          # device-to-device, ahead of the graph in stream order
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._stage_free[k] = ev
+        if self.autodecoder:
+            self.indices.copy_(indices, non_blocking=True)
+        self._push_weights()
+        self.graph.replay()
+        if self.optimizer is not None:
+            bump_param_epoch()
+        slot = t & 3
+        self._loss_host[slot].copy_(self.flat.extra[:8], non_blocking=True)
+        self._loss_done[slot].record(main)
+        self._ticket = t + 1
+        return t
+
+    def result(self, ticket):
+        """Blocks until iteration `ticket` has finished on the device and returns its loss scalars (loss, sdf, inter,
+        eikonal, normals, div, latent_reg, curv) as a list of 8 floats."""
+        if not (self._ticket - 4 < ticket < self._ticket):
+            raise ValueError("GraphedStep.result: ticket %d is no longer (or not yet) in flight" % ticket)
+        slot = ticket & 3
+        self._loss_done[slot].synchronize()
+        return self._loss_host[slot].tolist()

@@ -18,6 +18,7 @@ In scope: the tensor-core precision modes (bf16x2, bf16) and the loss types of t
 two-call API there (no silent fallback).
 """
 import ctypes
+import os
 
 import torch
 
@@ -115,6 +116,9 @@ def fused_step(net, criterion, mnfld_points, nonmnfld_points, mnfld_n_gt, latent
     L = _lib.lib()
     wbytes = L.digs_step_workspace_bytes(ctypes.byref(cnet), bs * n_n, bs * n_m, int(want_lap), mode)
     ws = torch.empty(max(int(wbytes), 16), dtype=torch.uint8, device=dev)
+    if os.environ.get("DIGS_B200_TRACE"):      # diagnostic builds (make DIAG=TRACE): keep the workspace for scripts/overlap_trace.py
+        global _trace_ws
+        _trace_ws = ws
     with torch.cuda.device(dev):
         rc = L.digs_step_fused(ctypes.byref(cnet), _ptr(xn), bs * n_n, _ptr(xm), bs * n_m, _ptr(nrm), d,
                                _ptr(sb), _ptr(sb), n_n, n_m, int(want_lap), ctypes.byref(cfg),
