@@ -107,6 +107,7 @@ struct SCfg {
     static constexpr int PLANE_FLOATS = PLANE_FLOATS_1 > PLANE_FLOATS_0 ? PLANE_FLOATS_1 : PLANE_FLOATS_0;
     static_assert(G0::N == G1::N && G0::B_BYTES == G1::B_BYTES && G0::TMEM_COLS == G1::TMEM_COLS, "clouds must share the operand tile");
     static_assert(G0::GP == 4 && G1::GP == 4, "jet tiles use 4-point groups");
+    static_assert(G0::T * 3 <= N * 3 / 2 && G1::T * 3 <= N * 3 / 2, "coordinates and normals share the staging block");
 };
 
 // L2 load that the compiler must leave where it is written (the plane prefetch of the NEXT item belongs at the end of the
@@ -152,6 +153,11 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const int64_t tl, ui
         sXyz[e * 3] = __ldg(xp);
         sXyz[e * 3 + 1] = __ldg(xp + 1);
         sXyz[e * 3 + 2] = (D > 2) ? __ldg(xp + 2) : 0.f;
+        if (sg.kind == 1 && sg.normals) {      // the loss section between the two directions is serial: its inputs are staged here
+            const float* np_ = sg.normals + gp * D;
+#pragma unroll
+            for (int k = 0; k < D; ++k) sXyz[N * 3 / 2 + e * D + k] = __ldg(np_ + k);
+        }
     }
     named_bar_sync(1, G::ETHREADS);
 
@@ -196,10 +202,21 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const int64_t tl, ui
                     const uint32_t t_base = t_buf + mt * N;
                     float bsum = 0.f, wlsum = 0.f, w0s0 = 0.f, w0s1 = 0.f, w0s2 = 0.f;
                     float acc[C][GP];
+                    // reverse hidden steps: sin / cos / |Z|^2 of the stored planes do not need the accumulators -- they run under
+                    // the TMEM load (the wait follows them); the empty asm pins every use of acc[] behind the wait
+                    constexpr bool kLateWaitDir = BWD;
+                    const bool late_wait = kLateWaitDir && l >= 1;
+                    auto acc_wait = [&]() {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+#pragma unroll
+                            for (int i = 0; i < GP; ++i) asm volatile("" : "+f"(acc[c][i]));
+                    };
                     if (j > 0) {
 #pragma unroll
                         for (int c = 0; c < C; ++c) tmem_ld4(t_base + c * T + g * GP, acc[c]);
-                        tmem_ld_wait();
+                        if (!late_wait) acc_wait();
                     }
                     float pre[C][GP];
                     if (l == 0) {
@@ -247,13 +264,19 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const int64_t tl, ui
                     }
                     // ---------------- per-point jet math ------------------------------------------------
                     float out[C][GP];
+                    float sn[GP], cs[GP], S2v[GP];
 #pragma unroll
                     for (int i = 0; i < GP; ++i) {
-                        float s, c;
-                        sincos_reduced(pre[0][i], s, c);
+                        sincos_reduced(pre[0][i], sn[i], cs[i]);
                         float S2 = 0.f;
 #pragma unroll
                         for (int k = 0; k < D; ++k) S2 = fmaf(pre[1 + k][i], pre[1 + k][i], S2);
+                        S2v[i] = S2;
+                    }
+                    if (late_wait && j > 0) acc_wait();
+#pragma unroll
+                    for (int i = 0; i < GP; ++i) {
+                        const float s = sn[i], c = cs[i], S2 = S2v[i];
                         const float Qp = LAP ? pre[C - 1][i] : 0.f;
                         if (!BWD) {
                             out[0][i] = s;
@@ -468,7 +491,7 @@ __device__ __forceinline__ void epi_tile(const StepArgs& a, const int64_t tl, ui
                     float nv[D], nn2 = 0.f, dot = 0.f;
 #pragma unroll
                     for (int k = 0; k < D; ++k) {
-                        nv[k] = __ldg(sg.normals + gp * D + k);
+                        nv[k] = sXyz[N * 3 / 2 + e * D + k];
                         nn2 = fmaf(nv[k], nv[k], nn2);
                         dot = fmaf(gr[k], nv[k], dot);
                     }
