@@ -234,8 +234,9 @@ def workload_config(args, world, cfg, n_local):
             "precision_mode": args.mode,
             "parallelism": par + "1 in-graph NCCL allreduce of the flat gradient buffer (+8 loss scalars)",
             "step_api": "eager two-call API (DiGSNetwork.forward / DiGSLoss / backward)" if args.no_graph else
-                        "digs_b200.GraphedStep: CUDA graph of zero-fill + operand prep + digs_step_fused (tile kernel + "
-                        "weight-gradient GEMM) + allreduce",
+                        "digs_b200.GraphedStep: CUDA graph of zero-fill + operand prep + digs_step_fused (counter reset, tile "
+                        "kernel, weight-gradient GEMM as a programmatic dependent launch that starts on the SMs the tile "
+                        "kernel frees in its last round) + allreduce",
             "l2": "256 MiB scratch written between timed steps (L2 flush); per-step events exclude the flush"}
 
 

@@ -86,18 +86,32 @@ class GraphedStep:
         torch.cuda.synchronize(dev)
         from . import _lib
         before = _lib.lib().digs_launch_count()
-        self.graph = torch.cuda.CUDAGraph()
-        fc.invalidate_prepared()        # the operand preparation must be recorded inside the graph
-        mode = "thread_local" if self.world > 1 else "global"   # NCCL's watchdog thread touches CUDA while we capture
-        with torch.cuda.graph(self.graph, capture_error_mode=mode):
-            self.loss_dict = self._body(warm=False)
+        self.graph, self.loss_dict = self._capture()
         self.launches_per_step = int(_lib.lib().digs_launch_count() - before)   # library kernels recorded in the graph
         self.loss_dict = {k: v.detach() for k, v in self.loss_dict.items()}
+
+    def _capture(self, host_in=None, host_loss=None, pool=None):
+        """Records one iteration.  With host_in / host_loss (pinned tensors) the graph starts with the host-to-device copy of
+        the batch and ends with the device-to-host copy of the eight loss scalars -- memcpy nodes INSIDE the graph (measured:
+        a separate copy between two graph launches costs 15-45 us of stream time each, scripts/e2e_probe.py)."""
+        fc = self.net.decoder.fc_block
+        graph = torch.cuda.CUDAGraph()
+        fc.invalidate_prepared()        # the operand preparation must be recorded inside the graph
+        mode = "thread_local" if self.world > 1 else "global"   # NCCL's watchdog thread touches CUDA while we capture
+        kw = {"pool": pool} if pool is not None else {}
+        with torch.cuda.graph(graph, capture_error_mode=mode, **kw):
+            if host_in is not None:
+                self._inputs.copy_(host_in, non_blocking=True)
+            loss_dict = self._body(warm=False)
+            if host_loss is not None:
+                host_loss.copy_(self.flat.extra[:8], non_blocking=True)
+        return graph, loss_dict
 
     def release(self):
         """Drop the captured graph.  Call this (or delete the object) BEFORE torch.distributed.destroy_process_group():
         tearing the NCCL communicator down while a graph that captured its kernels is alive blocks forever."""
         self.graph = None
+        self._io_graphs = [None, None]
 
     def pack_host_batch(self, mnfld_points, nonmnfld_points, mnfld_normals):
         """One pinned host tensor laid out like the static device inputs; returns (packed, mnfld, nonmnfld, normals) where the
@@ -208,63 +222,66 @@ class GraphedStep:
     # ---- pipelined host feed ---------------------------------------------------------------------------------------------
     # The reference feeds its loop from DataLoader workers (train_surface_reconstruction.py:44-46, 114-119: the batch of
     # iteration i+1 is prepared while iteration i runs) and reads the loss for logging.  submit() / result() are that loop
-    # shape without a host synchronisation per iteration: the host-to-device copy of batch i+1 runs on a copy stream while
-    # the graph of iteration i executes, and the loss of iteration i is read back asynchronously and handed out one call
-    # later.  Every iteration still pays its own copy in and its own read out.
+    # shape without a host synchronisation per iteration.  Two extra graphs are recorded, one per pinned staging buffer:
+    # each begins with the host-to-device copy of ITS staging buffer into the static inputs and ends with the device-to-host
+    # copy of the eight loss scalars into ITS pinned result slot, so an iteration is a single graph launch and the host may
+    # fill the other staging buffer while it runs.  Every iteration still pays its own copy in and its own read out.
     def _pipe_init(self):
-        dev = self._inputs.device
-        self._copy_stream = torch.cuda.Stream(device=dev)
-        self._stage = [torch.empty_like(self._inputs) for _ in range(2)]
-        self._stage_full = [torch.cuda.Event() for _ in range(2)]
-        self._stage_free = [None, None]
-        self._loss_host = torch.zeros(4, 8, dtype=torch.float32).pin_memory()
-        self._loss_done = [torch.cuda.Event() for _ in range(4)]
+        n_in = self._inputs.numel()
+        self._host_in = [torch.zeros(n_in, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._host_loss = [torch.zeros(8, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._io_graphs = [self._capture(self._host_in[k], self._host_loss[k], pool=self.graph.pool())[0] for k in range(2)]
+        self._io_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self._io_pending = [False, False]
         self._ticket = 0
+        torch.cuda.synchronize(self._inputs.device)
+
+    def staging(self, ticket=None):
+        """(mnfld, nonmnfld, normals) views of the pinned staging buffer the NEXT submit() will read (or the one of a given
+        future ticket): a data loader that writes its batch straight into them saves submit() the host-side copy."""
+        if not hasattr(self, "_io_graphs"):
+            self._pipe_init()
+        k = (self._ticket if ticket is None else ticket) & 1
+        buf = self._host_in[k]
+        o1, o2 = self.mnfld.numel(), self.mnfld.numel() + self.normals.numel()
+        return buf[:o1].view_as(self.mnfld), buf[o2:].view_as(self.nonmnfld), buf[o1:o2].view_as(self.normals)
 
     @torch.no_grad()
-    def submit(self, packed_host, indices=None):
-        """Queues one iteration on a pinned host batch in pack_host_batch layout (the `packed` tensor it returned) and
-        returns a ticket for result().  Does not wait for the device; at most two iterations are in flight (result() of
-        ticket t must be taken before submit() number t + 3 reuses its read-back slot)."""
+    def submit(self, packed_host=None, indices=None):
+        """Queues one iteration and returns a ticket for result().  `packed_host`: a host float32 tensor in pack_host_batch
+        layout (copied into the staging buffer), or None when the caller has filled staging() itself.  Does not wait for the
+        device unless two iterations are already in flight (then it waits for the older one: its staging buffer is reused)."""
         if self.sampler is not None:
             raise RuntimeError("GraphedStep.submit: this graph draws its batch on the device (sampler=); call step()")
-        if not hasattr(self, "_copy_stream"):
+        if not hasattr(self, "_io_graphs"):
             self._pipe_init()
-        if (packed_host.is_cuda or not packed_host.is_pinned() or packed_host.dtype != torch.float32
-                or packed_host.numel() != self._inputs.numel()):
-            raise ValueError("GraphedStep.submit: needs the pinned float32 tensor of pack_host_batch()")
+        if packed_host is not None and (packed_host.is_cuda or packed_host.dtype != torch.float32
+                                        or packed_host.numel() != self._inputs.numel()):
+            raise ValueError("GraphedStep.submit: needs a host float32 tensor in pack_host_batch() layout")
         if [p.data_ptr() for p in self.net.parameters()] != self._param_ptrs:
             raise RuntimeError("digs_b200.GraphedStep: parameter storage moved since capture")
         t = self._ticket
         k = t & 1
-        main = torch.cuda.current_stream(self._inputs.device)
-        with torch.cuda.stream(self._copy_stream):
-            if self._stage_free[k] is not None:
-                self._copy_stream.wait_event(self._stage_free[k])      # the iteration that used this buffer has consumed it
-            self._stage[k].copy_(packed_host.view(-1), non_blocking=True)
-            self._stage_full[k].record(self._copy_stream)
-        main.wait_event(self._stage_full[k])
-        self._inputs.copy_(self._stage[k], non_blocking=True)          # device-to-device, ahead of the graph in stream order
-        ev = torch.cuda.Event()
-        ev.record(main)
-        self._stage_free[k] = ev
+        if self._io_pending[k]:
+            self._io_done[k].synchronize()          # iteration t - 2 still owns this staging buffer / result slot
+        if packed_host is not None:
+            self._host_in[k].copy_(packed_host.view(-1))
         if self.autodecoder:
             self.indices.copy_(indices, non_blocking=True)
         self._push_weights()
-        self.graph.replay()
+        self._io_graphs[k].replay()
+        self._io_done[k].record(torch.cuda.current_stream(self._inputs.device))
+        self._io_pending[k] = True
         if self.optimizer is not None:
             bump_param_epoch()
-        slot = t & 3
-        self._loss_host[slot].copy_(self.flat.extra[:8], non_blocking=True)
-        self._loss_done[slot].record(main)
         self._ticket = t + 1
         return t
 
     def result(self, ticket):
         """Blocks until iteration `ticket` has finished on the device and returns its loss scalars (loss, sdf, inter,
-        eikonal, normals, div, latent_reg, curv) as a list of 8 floats."""
-        if not (self._ticket - 4 < ticket < self._ticket):
+        eikonal, normals, div, latent_reg, curv) as a list of 8 floats.  Only the two most recent tickets are kept."""
+        if not hasattr(self, "_io_graphs") or not (self._ticket - 2 <= ticket < self._ticket):
             raise ValueError("GraphedStep.result: ticket %d is no longer (or not yet) in flight" % ticket)
-        slot = ticket & 3
-        self._loss_done[slot].synchronize()
-        return self._loss_host[slot].tolist()
+        k = ticket & 1
+        self._io_done[k].synchronize()
+        return self._host_loss[k].tolist()
