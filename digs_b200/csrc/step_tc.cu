@@ -845,8 +845,14 @@ int step_fused(const DigsNet* net, const float* nonmnfld, int64_t nn, const floa
     a.scratch_stride = (int64_t)L.scratch_stride;
     // tile-round counters for the overlapped weight-gradient GEMM (DIGS_B200_WGRAD_OVERLAP=0: plain stream order)
     const int grid_ctas = (int)(L.total_tiles < num_sms() ? L.total_tiles : num_sms());
-    bool overlap = (L.total_tiles + grid_ctas - 1) / grid_ctas <= WG_QUEUE_IDX;
-    if (const char* e = getenv("DIGS_B200_WGRAD_OVERLAP")) overlap = overlap && e[0] != '0';
+    // Worth it only when the last round leaves a visible share of the SMs idle (C2: 1094 tiles = 7.4 rounds on 148 CTAs, 7.6 %
+    // of the kernel's SM time; C4 / C5: 14.8 rounds, 1.5 % -- there the finer work units of the overlapped GEMM cost more
+    // than the tail returns: measured +2 % / +0.5 % step time).  DIGS_B200_WGRAD_OVERLAP=0 / 1 forces either way.
+    const int64_t rounds = (L.total_tiles + grid_ctas - 1) / grid_ctas;
+    const double idle_share = (double)(rounds * grid_ctas - L.total_tiles) / (double)(rounds * grid_ctas);
+    bool overlap = idle_share >= 0.03;
+    if (const char* e = getenv("DIGS_B200_WGRAD_OVERLAP")) overlap = (e[0] != '0');
+    overlap = overlap && rounds <= WG_QUEUE_IDX;
     if (const char* e = getenv("DIGS_B200_STEP_NO_WGRAD")) overlap = overlap && e[0] != '1';
     if (overlap) {
         a.round_ctr = reinterpret_cast<unsigned int*>(w + prep_ws_bytes(net) + 2 * L.words_bytes + L.scratch_bytes);

@@ -13,7 +13,8 @@
 //
 // CTA (split, tile, layer) owns a 256 x 256 (m', n') = 128 x 128 (u, k) output tile and a K range, accumulates it in
 // all 512 TMEM columns over a 3-stage TMA ring and adds it to the gradient with fp32 vector reductions.
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue (two warps per TMEM
+// lane quarter, each draining half of the accumulator columns).
 //
 // Behind the fused step (step_tc.cu) the launch is a programmatic dependent launch: the persistent tile kernel walks its
 // tiles in rounds of gridDim.x, the last round is partial (C2: 1094 tiles on 148 CTAs = 7 full rounds + 58 tiles), and
@@ -31,7 +32,7 @@ namespace tcpath {
 
 using namespace digs::tc;
 
-constexpr int WG_THREADS = 192;
+constexpr int WG_THREADS = 320;             // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int WG_BOX = 64 * 64 * 2;            // one TMA box: 64 split rows x 64 columns, bf16
 constexpr int WG_OPER = 4 * WG_BOX;            // one operand tile: 256 split rows x 64 columns
 constexpr int WG_STAGE = 2 * WG_OPER;          // A + B
@@ -88,9 +89,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(const __grid_constan
     uint64_t* full = bars;
     uint64_t* empty = bars + WG_STAGES;
     uint64_t* acc_bar = bars + 2 * WG_STAGES;           // accumulators of the current unit complete (tcgen05.commit)
-    uint64_t* acc_free = bars + 2 * WG_STAGES + 1;      // ... and read out by the 128 epilogue threads
+    uint64_t* acc_free = bars + 2 * WG_STAGES + 1;      // ... and read out by the 256 epilogue threads
     uint64_t* unit_ready = bars + 2 * WG_STAGES + 2;    // [2]: s_unit[i & 1] published by the producer
-    uint64_t* unit_free = bars + 2 * WG_STAGES + 4;     // [2]: ... and read by the MMA thread and the 128 epilogue threads
+    uint64_t* unit_free = bars + 2 * WG_STAGES + 4;     // [2]: ... and read by the MMA thread and the 256 epilogue threads
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 6);
     volatile int* s_unit = reinterpret_cast<volatile int*>(tmem_slot + 2);
 
@@ -105,11 +106,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(const __grid_constan
     if (tid == 0) {
         for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(acc_bar, 1);
-        mbar_init(acc_free, 128);
+        mbar_init(acc_free, 256);
         mbar_init(&unit_ready[0], 1);
         mbar_init(&unit_ready[1], 1);
-        mbar_init(&unit_free[0], 129);
-        mbar_init(&unit_free[1], 129);
+        mbar_init(&unit_free[0], 257);
+        mbar_init(&unit_free[1], 257);
         fence_barrier_init();
         tma_prefetch_desc(&tmapG);
         tma_prefetch_desc(&tmapA);
@@ -218,7 +219,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(const __grid_constan
             }
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3;                         // TMEM lane quarter this warp may read
+        const int chalf = (warp - 2) >> 2;              // which half of the 256 accumulator columns of each M block
         const int part = lane & 1;
         int done = 0;
         for (int i = 0;; ++i) {
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(const __grid_constan
                 const int uu = mt * 128 + m * 64 + q * 16 + (lane >> 1);
                 float* dst = a.dW[li + 1] + (int64_t)uu * a.H + nt * 128;
 #pragma unroll 4
-                for (int c0 = 0; c0 < 256; c0 += 8) {
+                for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 8) {
                     float v[8];
                     tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + m * 256 + c0, v);
                     tmem_ld_wait();
