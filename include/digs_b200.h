@@ -157,6 +157,10 @@ int digs_loss_fused_dw(const float* f_m, const float* g_m, int64_t nm, const flo
  *   cfg: loss configuration (weights on the host or, for CUDA-graph replays, in device memory; global point counts).
  *   outputs f_n (nn), g_n (nn,d), lap_n (nn or NULL), f_m (nm), g_m (nm,d); terms_out[8] as digs_loss_fused (accumulated).
  *   grads: accumulated (+=) like digs_jet_backward.
+ * The GEMM is a programmatic dependent launch where that pays: the persistent tile kernel leaves part of the SMs idle in its
+ * last round of tiles, the GEMM's CTAs start there and synchronise on per-round completion counters in the workspace (reset by
+ * a memset on `stream` in front of the tile kernel) instead of on the whole grid; work queued on `stream` after this call sees
+ * both launches complete.  Results do not depend on it (DIGS_B200_WGRAD_OVERLAP=0 forces plain stream order).
  * DIGS_MODE_FP32 returns DIGS_ENOTIMPL (the two-call API covers it). */
 typedef struct DigsLossCfg {
     float weights[6];            /* sdf, inter, normal, eikonal, div, latent (host copy) */
