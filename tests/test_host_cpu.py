@@ -245,3 +245,24 @@ def test_data_parallel_reduction_gloo_world2(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, out.decode()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): ONE JSON line on stdout with the same metric /
+    unit / direction as our arm, `impl: reference`, a truthful CPU config, zero copy bytes and no GPU launches."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "5", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "train points/sec (value+grad+div+backward)" and d["unit"] == "points/s"
+    assert d["higher_is_better"] is True and d["steps"] == 5 and d["warmup"] == 3 and d["gpu_launches"] == 0
+    assert d["value"] > 0 and abs(d["value"] - d["e2e"]["value"]) < 1e-6 * d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert "GraphedStep" not in json.dumps(d["config"]) and "bf16" not in d["config"]["precision_mode"]
