@@ -346,33 +346,40 @@ def time_config(args, cfg, dev, rank, world, steps, warmup, with_e2e=True):
         launches = graphed.launches_per_step      # library kernels recorded in (and replayed from) the graph each step
     ms_dev = sum(a.elapsed_time(b) for a, b in evs) / steps
     ms_e2e, ms_e2e_sync, d2h_bytes = 0.0, 0.0, 4
+    E2E_BLOCKS = 3          # the K-step end-to-end loop is a ~20 ms wall-clock interval: repeat it and report the median block
     if with_e2e:
         for i in range(min(warmup, 3)):
             float(run(hb[i]).item())
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(steps):
-            float(run(hb[warmup + i]).item())      # pinned host batch in, loss scalar out, host blocks on every step
-        barrier()
-        ms_e2e = ms_e2e_sync = 1e3 * (time.perf_counter() - t0) / steps
+        blocks = []
+        for _ in range(E2E_BLOCKS):
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                float(run(hb[warmup + i]).item())      # pinned host batch in, loss scalar out, host blocks on every step
+            barrier()
+            blocks.append(1e3 * (time.perf_counter() - t0) / steps)
+        ms_e2e = ms_e2e_sync = float(np.median(blocks))
         if graphed is not None:
             # the same K steps with the host feed pipelined the way the reference's DataLoader workers feed its loop: the copy
             # of batch i+1 overlaps step i, the loss of step i is read back asynchronously and consumed one step later
             for i in range(min(warmup, 3)):
                 graphed.result(graphed.submit(packed[i], indices=idx))
-            barrier()
-            losses, prev = [], None
-            t0 = time.perf_counter()
-            for i in range(steps):
-                tk = graphed.submit(packed[warmup + i], indices=idx)
-                if prev is not None:
-                    losses.append(graphed.result(prev)[0])
-                prev = tk
-            losses.append(graphed.result(prev)[0])
-            barrier()
-            ms_e2e = 1e3 * (time.perf_counter() - t0) / steps
+            blocks = []
+            for _ in range(E2E_BLOCKS):
+                barrier()
+                losses, prev = [], None
+                t0 = time.perf_counter()
+                for i in range(steps):
+                    tk = graphed.submit(packed[warmup + i], indices=idx)
+                    if prev is not None:
+                        losses.append(graphed.result(prev)[0])
+                    prev = tk
+                losses.append(graphed.result(prev)[0])
+                barrier()
+                blocks.append(1e3 * (time.perf_counter() - t0) / steps)
+                assert len(losses) == steps and all(np.isfinite(v) for v in losses)
+            ms_e2e = float(np.median(blocks))
             d2h_bytes = 32
-            assert len(losses) == steps and all(np.isfinite(v) for v in losses)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_dev, ms_e2e, ms_e2e_sync], dtype=torch.float64, device=dev)
     if world > 1:
@@ -569,8 +576,10 @@ def run_ours(args, rank, world, local_rank):
                 "data": "synthetic", "config": workload_config(args, world, cfg, n_local),
                 "e2e": {"value": pts / (ms_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": res["h2d_bytes"],
                         "d2h_bytes_per_step": res["d2h_bytes"], "ms_per_step": ms_e2e,
-                        "host_feed": "GraphedStep.submit / result: pinned host batch -> device on a copy stream while the "
-                                     "previous step runs, 8 loss scalars read back per step and consumed one step later",
+                        "host_feed": "GraphedStep.submit / result: one graph launch per step whose first node copies the pinned "
+                                     "host batch to the device and whose last node copies the 8 loss scalars back; two such "
+                                     "graphs alternate over two staging buffers, the loss is consumed one step later",
+                        "timing": "wall clock over the K steps, median of 3 such blocks",
                         "blocking_ms_per_step": res["ms_e2e_sync"],
                         "blocking_value": pts / (res["ms_e2e_sync"] * 1e-3) if res["ms_e2e_sync"] > 0 else None},
                 "gpu_launches": res["launches"], "clocks": res["clocks"]}
