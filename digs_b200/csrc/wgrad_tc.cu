@@ -11,17 +11,19 @@
 // in separate accumulators; the epilogue adds each 2x2 block into one fp32 gradient entry.  TMA boxes of 64 split rows
 // x 64 columns with SWIZZLE_128B land directly in the canonical MN-major UMMA layout (LBO = 8192, SBO = 1024).
 //
-// CTA (split, tile, layer) owns a 256 x 256 (m', n') = 128 x 128 (u, k) output tile and a K range, accumulates it in
-// all 512 TMEM columns over a 3-stage TMA ring and adds it to the gradient with fp32 vector reductions.
+// A work unit (K split, layer, output tile) is a 256 x 256 (m', n') = 128 x 128 (u, k) output tile over a K range: it is
+// accumulated in all 512 TMEM columns over a 3-stage TMA ring and added to the gradient with fp32 vector reductions.
+// Plain launch (two-call API): one unit per CTA.  Behind the fused step: a persistent grid draws units from a queue.
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue (two warps per TMEM
 // lane quarter, each draining half of the accumulator columns).
 //
 // Behind the fused step (step_tc.cu) the launch is a programmatic dependent launch: the persistent tile kernel walks its
 // tiles in rounds of gridDim.x, the last round is partial (C2: 1094 tiles on 148 CTAs = 7 full rounds + 58 tiles), and
-// the CTAs without a tile in it exit early.  The GEMM's CTAs are dispatched onto those SMs, split index slowest, so the
-// first ones own the K ranges (operand columns) of the early rounds; each waits on the per-round completion counters the
-// tile kernel publishes (release / acquire at gpu scope) instead of on the whole grid.  The CTAs of the last split also
-// wait for every tile-kernel CTA to have finished, so that completion of this grid implies completion of that one.
+// the CTAs without a tile in it exit early.  The GEMM's CTAs are dispatched onto those SMs and draw units split index
+// slowest, so the first units cover the K ranges (operand columns) of the early rounds; each unit waits on the per-round
+// completion counters the tile kernel publishes (release / acquire at gpu scope) instead of on the whole grid.  The units
+// of the last split also wait for every tile-kernel CTA to have finished, so that completion of this grid implies
+// completion of that one.  (Timeline and A/B numbers: profiles/r02b_experiments.md.)
 #include "digs_internal.h"
 #include "tc_common.cuh"
 #include <cuda.h>
