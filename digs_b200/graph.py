@@ -242,6 +242,8 @@ class GraphedStep:
         if not hasattr(self, "_io_graphs"):
             self._pipe_init()
         k = (self._ticket if ticket is None else ticket) & 1
+        if self._io_pending[k]:
+            self._io_done[k].synchronize()          # the iteration that last read this buffer must have finished
         buf = self._host_in[k]
         o1, o2 = self.mnfld.numel(), self.mnfld.numel() + self.normals.numel()
         return buf[:o1].view_as(self.mnfld), buf[o2:].view_as(self.nonmnfld), buf[o1:o2].view_as(self.normals)
